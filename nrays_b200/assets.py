@@ -171,15 +171,19 @@ def _mtl(name, seed, tex=None, opacity=None, alpha=1.0, ns=60.0):
 SPONZA_TARGET_TRIS = 262144
 
 
-def sponza_standin(seed=0, target_tris=SPONZA_TARGET_TRIS):
+def sponza_standin(seed=0, target_tris=SPONZA_TARGET_TRIS, lod=1):
     """Procedural atrium standing in for media/crytek-sponza/sponza.obj.
 
     OBJ-space bounds ~ (+-1900, 0..1500, +-1200) (the loader divides by 4), two colonnade storeys with
     arches on both long sides, tessellated floor / walls / gallery slabs, hanging drapes, vases and
     two alpha-masked foliage groups (map_d).  Returns (ObjData, textures) where `textures` maps the
     MTL texture paths to decoded uint8 images.  Triangle count == target_tris exactly (the floor
-    tessellation absorbs the remainder).
+    tessellation absorbs the remainder).  `lod` > 1 divides every fixed tessellation count (small test
+    scenes: lod=4 leaves ~15 k fixed triangles).
     """
+    def q(n):
+        return max(2, int(n) // int(lod))
+
     rng = np.random.default_rng(seed)
     textures = {}
     for i, kind in enumerate(["brick", "tile", "cloth", "brick", "tile", "cloth"]):
@@ -193,27 +197,27 @@ def sponza_standin(seed=0, target_tris=SPONZA_TARGET_TRIS):
     Y1, Y2 = 520.0, 1040.0  # gallery floor heights
 
     # walls (4 groups, textured)
-    mb.add("wall_north", _mtl("wall_n", 1, "textures/std_0.png"), [_grid((X0, 0, Z1), (X1 - X0, 0, 0), (0, H, 0), 96, 40, (12, 5))])
-    mb.add("wall_south", _mtl("wall_s", 2, "textures/std_0.png"), [_grid((X1, 0, Z0), (X0 - X1, 0, 0), (0, H, 0), 96, 40, (12, 5))])
-    mb.add("wall_east", _mtl("wall_e", 3, "textures/std_3.png"), [_grid((X1, 0, Z1), (0, 0, Z0 - Z1), (0, H, 0), 64, 40, (8, 5))])
-    mb.add("wall_west", _mtl("wall_w", 4, "textures/std_3.png"), [_grid((X0, 0, Z0), (0, 0, Z1 - Z0), (0, H, 0), 64, 40, (8, 5))])
+    mb.add("wall_north", _mtl("wall_n", 1, "textures/std_0.png"), [_grid((X0, 0, Z1), (X1 - X0, 0, 0), (0, H, 0), q(96), q(40), (12, 5))])
+    mb.add("wall_south", _mtl("wall_s", 2, "textures/std_0.png"), [_grid((X1, 0, Z0), (X0 - X1, 0, 0), (0, H, 0), q(96), q(40), (12, 5))])
+    mb.add("wall_east", _mtl("wall_e", 3, "textures/std_3.png"), [_grid((X1, 0, Z1), (0, 0, Z0 - Z1), (0, H, 0), q(64), q(40), (8, 5))])
+    mb.add("wall_west", _mtl("wall_w", 4, "textures/std_3.png"), [_grid((X0, 0, Z0), (0, 0, Z1 - Z0), (0, H, 0), q(64), q(40), (8, 5))])
     # ceiling ring (open roof in the middle, closed above galleries)
     mb.add("roof", _mtl("roof", 5), [
-        _grid((X0, H, ZI), (X1 - X0, 0, 0), (0, 0, Z1 - ZI), 64, 12),
-        _grid((X0, H, Z0), (X1 - X0, 0, 0), (0, 0, -ZI - Z0), 64, 12),
+        _grid((X0, H, ZI), (X1 - X0, 0, 0), (0, 0, Z1 - ZI), q(64), q(12)),
+        _grid((X0, H, Z0), (X1 - X0, 0, 0), (0, 0, -ZI - Z0), q(64), q(12)),
     ])
     # gallery slabs (two storeys x two sides), each a top and a bottom sheet
     slabs = []
     for y in (Y1, Y2):
         for z0, z1 in ((ZI, Z1), (Z0, -ZI)):
-            slabs.append(_grid((X0, y, z0), (X1 - X0, 0, 0), (0, 0, z1 - z0), 80, 12, (10, 2)))
-            slabs.append(_grid((X0, y - 40.0, z0), (0, 0, z1 - z0), (X1 - X0, 0, 0), 12, 80, (2, 10)))
+            slabs.append(_grid((X0, y, z0), (X1 - X0, 0, 0), (0, 0, z1 - z0), q(80), q(12), (10, 2)))
+            slabs.append(_grid((X0, y - 40.0, z0), (0, 0, z1 - z0), (X1 - X0, 0, 0), q(12), q(80), (2, 10)))
     mb.add("gallery_slabs", _mtl("slabs", 6, "textures/std_4.png"), slabs)
 
     # columns: 3 storeys x 2 sides x ncol, surfaces of revolution with entasis + capital
     ncol = 14
     xs = np.linspace(X0 + 160.0, X1 - 160.0, ncol)
-    prof_t = np.linspace(0, 1, 17)
+    prof_t = np.linspace(0, 1, q(16) + 1)
     for storey, (yb, yt) in enumerate(((0.0, Y1 - 40.0), (Y1, Y2 - 40.0), (Y2, H))):
         cols = []
         rad = 46.0 - 6.0 * storey
@@ -221,7 +225,7 @@ def sponza_standin(seed=0, target_tris=SPONZA_TARGET_TRIS):
             for x in xs:
                 r = rad * (1.0 - 0.12 * prof_t + 0.35 * np.exp(-((prof_t - 1.0) / 0.05) ** 2) +
                            0.3 * np.exp(-(prof_t / 0.04) ** 2))
-                cols.append(_revolve((x, yb, side * ZI), r, prof_t * (yt - yb), 24))
+                cols.append(_revolve((x, yb, side * ZI), r, prof_t * (yt - yb), q(24)))
         mb.add("columns_%d" % storey, _mtl("col%d" % storey, 10 + storey, "textures/std_%d.png" % (1 if storey else 3), ns=80.0), cols)
 
     # arches between neighbouring columns, each storey / side
@@ -230,7 +234,7 @@ def sponza_standin(seed=0, target_tris=SPONZA_TARGET_TRIS):
         for side in (-1.0, 1.0):
             for i in range(ncol - 1):
                 arches.append(_arch((xs[i], side * ZI - 30.0), (xs[i + 1], side * ZI - 30.0), ytop - 170.0, 150.0, 20.0,
-                                    (0.0, 0.0, 60.0), 32))
+                                    (0.0, 0.0, 60.0), q(32)))
         mb.add("arches_%d" % storey, _mtl("arch%d" % storey, 20 + storey, "textures/std_0.png"), arches)
 
     # drapes: wavy cloth sheets hanging between first-storey columns (4 materials)
@@ -245,17 +249,17 @@ def sponza_standin(seed=0, target_tris=SPONZA_TARGET_TRIS):
                     return np.stack([np.zeros_like(S), -18.0 * np.sin(np.pi * S) * T, side * w], -1)
 
                 drapes.append(_grid((xs[i] + 40.0, Y1 - 60.0, side * (ZI - 70.0)), (xs[i + 1] - xs[i] - 80.0, 0, 0),
-                                    (0, -330.0, 0), 32, 24, (3, 3), disp))
+                                    (0, -330.0, 0), q(32), q(24), (3, 3), disp))
         mb.add("drape_%d" % k, _mtl("drape%d" % k, 30 + k, "textures/std_%d.png" % (2 if k % 2 else 5), ns=20.0), drapes)
 
     # vases on the floor (2 materials)
     for k in range(2):
         vases = []
-        pt = np.linspace(0, 1, 17)
+        pt = np.linspace(0, 1, q(16) + 1)
         for x in xs[k::2]:
             for side in (-1.0, 1.0):
                 r = 30.0 + 45.0 * np.sin(np.pi * pt) ** 2 * (1.0 - 0.4 * pt)
-                vases.append(_revolve((x, 0.0, side * (ZI - 200.0)), r, pt * 170.0, 32))
+                vases.append(_revolve((x, 0.0, side * (ZI - 200.0)), r, pt * 170.0, q(32)))
         mb.add("vases_%d" % k, _mtl("vase%d" % k, 40 + k, ns=120.0), vases)
 
     # alpha-masked foliage: crossed quads, densely tessellated, two groups with map_d
@@ -266,7 +270,7 @@ def sponza_standin(seed=0, target_tris=SPONZA_TARGET_TRIS):
                 c = np.array([x, 170.0, side * (ZI - 200.0)])
                 for a in (0.0, np.pi / 3, 2 * np.pi / 3):
                     d = np.array([np.cos(a), 0.0, np.sin(a)]) * 240.0
-                    leaves.append(_grid(c - 0.5 * d, d, (0, 260.0, 0), 10, 10, (2, 2)))
+                    leaves.append(_grid(c - 0.5 * d, d, (0, 260.0, 0), q(10), q(10), (2, 2)))
         mb.add("foliage_%d" % k, _mtl("leaf%d" % k, 50 + k, "textures/std_%d.png" % (1 + k), "textures/leaf_mask_%d.png" % k), leaves)
 
     # a lion-head-like bumpy relief on the far wall + a few banners to diversify materials
@@ -274,11 +278,11 @@ def sponza_standin(seed=0, target_tris=SPONZA_TARGET_TRIS):
         return np.stack([-(60.0 * np.exp(-(((S - 0.5) / 0.22) ** 2 + ((T - 0.5) / 0.22) ** 2)) *
                            (1.0 + 0.3 * np.sin(24 * S) * np.sin(24 * T))), np.zeros_like(S), np.zeros_like(S)], -1)
 
-    mb.add("relief", _mtl("relief", 60, ns=40.0), [_grid((X1 - 5.0, 300.0, -250.0), (0, 0, 500.0), (0, 500.0, 0), 96, 96, (1, 1), bump)])
+    mb.add("relief", _mtl("relief", 60, ns=40.0), [_grid((X1 - 5.0, 300.0, -250.0), (0, 0, 500.0), (0, 500.0, 0), q(96), q(96), (1, 1), bump)])
     for k in range(3):
         zb = -300.0 + 300.0 * k
         mb.add("banner_%d" % k, _mtl("banner%d" % k, 70 + k, "textures/std_2.png", ns=15.0),
-               [_grid((X0 + 400.0 + 900.0 * k, 1400.0, zb - 60.0), (0, 0, 120.0), (0, -620.0, 0), 16, 64, (1, 4),
+               [_grid((X0 + 400.0 + 900.0 * k, 1400.0, zb - 60.0), (0, 0, 120.0), (0, -620.0, 0), q(16), q(64), (1, 4),
                       lambda S, T: np.stack([14.0 * np.sin(4 * np.pi * T + S), np.zeros_like(S), np.zeros_like(S)], -1))])
 
     # floor last: its tessellation absorbs the remaining triangle budget exactly

@@ -118,9 +118,9 @@ def hairball_text():
               material="default", refl=(0.0, 0.0))])
 
 
-def sponza_resolver(seed=0, target_tris=assets.SPONZA_TARGET_TRIS):
+def sponza_resolver(seed=0, target_tris=assets.SPONZA_TARGET_TRIS, lod=1):
     r = AssetResolver()
-    od, tex = assets.sponza_standin(seed, target_tris)
+    od, tex = assets.sponza_standin(seed, target_tris, lod)
     r.objs["media/crytek-sponza/sponza.obj"] = od
     for k, v in tex.items():
         r.textures["media/crytek-sponza/" + k] = v

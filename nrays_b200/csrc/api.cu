@@ -1,0 +1,789 @@
+// api.cu — C-ABI of include/nrays_b200.h: scene upload (Scene::new, src/scene.rs:119-133) and the
+// wavefront driver that replaces scene::render (src/scene.rs:29-116).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/nrays_b200.h"
+#include "bvh_build.h"
+#include "kernels.h"
+
+using namespace nrb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return fail(NRB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                \
+  } while (0)
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  cudaError_t ensure(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <class T>
+  T *as() const {
+    return reinterpret_cast<T *>(p);
+  }
+};
+
+template <class T>
+cudaError_t upload(DevBuf &b, const std::vector<T> &v) {
+  size_t n = std::max<size_t>(v.size() * sizeof(T), 16);
+  cudaError_t e = b.ensure(n);
+  if (e != cudaSuccess) return e;
+  if (!v.empty()) e = cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+
+size_t env_size(const char *name, size_t dflt) {
+  const char *s = getenv(name);
+  if (!s || !*s) return dflt;
+  return (size_t)strtoull(s, nullptr, 10);
+}
+
+}  // namespace
+
+struct NrbScene {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  // scene tables
+  DevBuf d_nodes, d_tris, d_tri_uvs, d_shapes, d_node_info, d_materials, d_textures, d_texels, d_lights, d_planes,
+      d_candidates;
+  SceneView view{};
+  bool has_shapes = false;
+  int child_factor = 0;  // max secondary rays per ray (reflection + refraction possible in this scene)
+  uint64_t n_bvh_nodes = 0, n_tris = 0, scene_bytes = 0;
+  int grid_closest = 148, grid_shadow = 148;
+  // frame state
+  DevBuf d_q[2][3], d_hits, d_sq[3], d_accum, d_counters, d_out, d_out8;
+  uint32_t q_cap[2] = {0, 0}, sq_cap = 0, hits_cap = 0;
+  Counters *h_counters = nullptr;  // pinned mirror
+  std::vector<cudaEvent_t> events;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+
+  ~NrbScene() {
+    cudaSetDevice(device);
+    if (h_counters) cudaFreeHost(h_counters);
+    for (auto e : events) cudaEventDestroy(e);
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_end) cudaEventDestroy(ev_end);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Scene::new — flatten + BVH build + upload
+// ---------------------------------------------------------------------------------------------
+bool shape_has_uv(int kind) { return kind == NRB_SHAPE_BALL || kind == NRB_SHAPE_CUBOID || kind == NRB_SHAPE_TRIMESH; }
+
+int relayout_bfs(std::vector<BvhNode> &nodes, int &root_all, int &root_opaque, std::vector<Candidate> &cands) {
+  // Level-order relabel from root_all so the top of the tree is one contiguous prefix of the array
+  // (what the closest-hit kernel touches for every ray; also the part worth staging on chip).
+  if (root_all < 0 || root_all == kEmpty || nodes.empty()) return 0;
+  std::vector<int> remap(nodes.size(), -1), order;
+  order.reserve(nodes.size());
+  order.push_back(root_all);
+  remap[root_all] = 0;
+  for (size_t head = 0; head < order.size(); ++head) {
+    const BvhNode &n = nodes[order[head]];
+    int ch[2] = {n.n3.x, n.n3.y};
+    for (int c : ch)
+      if (c >= 0 && remap[c] < 0) {
+        remap[c] = (int)order.size();
+        order.push_back(c);
+      }
+  }
+  std::vector<BvhNode> out(order.size());
+  for (size_t i = 0; i < order.size(); ++i) {
+    BvhNode n = nodes[order[i]];
+    if (n.n3.x >= 0) n.n3.x = remap[n.n3.x];
+    if (n.n3.y >= 0) n.n3.y = remap[n.n3.y];
+    out[i] = n;
+  }
+  auto fix = [&](int &c) {
+    if (c >= 0 && c != kEmpty) c = remap[c];
+  };
+  fix(root_all);
+  fix(root_opaque);
+  for (auto &c : cands) fix(c.root);
+  nodes.swap(out);
+  return 0;
+}
+
+int build_scene(const NrbSceneDesc &d, NrbScene &S) {
+  if (d.n_nodes && !d.nodes) return fail(NRB_ERR_INVALID_ARG, "nodes is NULL");
+  if (d.n_lights && !d.lights) return fail(NRB_ERR_INVALID_ARG, "lights is NULL");
+  if (d.n_materials == 0 || !d.materials) return fail(NRB_ERR_INVALID_ARG, "scene has no materials");
+  if (d.n_texels >= 0xFFFFFFFFull) return fail(NRB_ERR_INVALID_ARG, "texel pool too large (>= 2^32 texels)");
+
+  std::vector<Texture> textures(d.n_textures);
+  for (uint32_t i = 0; i < d.n_textures; ++i) {
+    const NrbTextureDesc &t = d.textures[i];
+    // ImageData::new asserts dims >= 1 and len == w*h (src/texture2d.rs:17-19)
+    if (t.width < 1 || t.height < 1 || t.texel_offset + (uint64_t)t.width * t.height > d.n_texels)
+      return fail(NRB_ERR_INVALID_ARG, "texture " + std::to_string(i) + " outside the texel pool");
+    if ((t.interpolation != NRB_INTERP_BILINEAR && t.interpolation != NRB_INTERP_NEAREST) ||
+        (t.overflow != NRB_OVERFLOW_CLAMP && t.overflow != NRB_OVERFLOW_WRAP))
+      return fail(NRB_ERR_INVALID_ARG, "texture " + std::to_string(i) + " has an unknown sampling mode");
+    textures[i] = Texture{t.width, t.height, t.interpolation, t.overflow, (uint32_t)t.texel_offset,
+                          (uint32_t)(d.n_texels - t.texel_offset)};
+  }
+  std::vector<Material> materials(d.n_materials);
+  for (uint32_t i = 0; i < d.n_materials; ++i) {
+    const NrbMaterialDesc &m = d.materials[i];
+    if (m.kind != NRB_MAT_PHONG && m.kind != NRB_MAT_NORMAL && m.kind != NRB_MAT_UV)
+      return fail(NRB_ERR_UNSUPPORTED, "material " + std::to_string(i) + ": only Phong / Normal / UV cross the C-ABI");
+    if (m.texture >= (int)d.n_textures || m.alpha_texture >= (int)d.n_textures)
+      return fail(NRB_ERR_INVALID_ARG, "material " + std::to_string(i) + " texture index out of range");
+    Material mm{};
+    mm.kind = m.kind;
+    for (int k = 0; k < 3; ++k) mm.ambient[k] = m.ambient[k], mm.diffuse[k] = m.diffuse[k], mm.specular[k] = m.specular[k];
+    mm.shininess = m.shininess;
+    mm.tex = m.kind == NRB_MAT_PHONG ? m.texture : -1;
+    mm.alpha_tex = m.kind == NRB_MAT_PHONG ? m.alpha_texture : -1;
+    materials[i] = mm;
+  }
+  std::vector<Light> lights(d.n_lights);
+  int shadow_samples = 0;
+  for (uint32_t i = 0; i < d.n_lights; ++i) {
+    const NrbLightDesc &l = d.lights[i];
+    if (l.racsample == 0 || l.racsample > 255)
+      return fail(NRB_ERR_INVALID_ARG, "light " + std::to_string(i) + ": racsample must be in [1, 255]");
+    Light L{};
+    for (int k = 0; k < 3; ++k) L.pos[k] = (float)l.pos[k], L.color[k] = l.color[k];
+    L.radius = (float)l.radius;
+    L.racsample = l.racsample;
+    lights[i] = L;
+    shadow_samples += (int)(l.racsample * l.racsample);
+  }
+  if (d.n_lights > 65535) return fail(NRB_ERR_INVALID_ARG, "too many lights (> 65535)");
+
+  // ---- nodes -------------------------------------------------------------------------------
+  std::vector<NodeInfo> node_info(d.n_nodes);
+  std::vector<Shape> shapes;
+  std::vector<int> planes;
+  std::vector<int> shape_of_node(d.n_nodes, -1);
+  std::vector<char> is_cand(d.n_nodes, 0);
+  bool any_refl = false, any_refr = false;
+  uint64_t total_tris = 0;
+  for (uint32_t i = 0; i < d.n_nodes; ++i) {
+    const NrbNodeDesc &n = d.nodes[i];
+    if (n.material < 0 || n.material >= (int)d.n_materials)
+      return fail(NRB_ERR_INVALID_ARG, "node " + std::to_string(i) + " material index out of range");
+    if (n.shape < NRB_SHAPE_BALL || n.shape > NRB_SHAPE_TRIMESH)
+      return fail(NRB_ERR_INVALID_ARG, "node " + std::to_string(i) + " has an unknown shape kind");
+    if (n.nmap_texture >= 0)
+      return fail(NRB_ERR_UNSUPPORTED, "node " + std::to_string(i) +
+                                           ": nmap depth shift (src/scene_node.rs:60-70) is not supported on device "
+                                           "(the reference loader never enables it: loader3d.rs:553)");
+    const Material &m = materials[n.material];
+    bool cand = (n.alpha < 1.0f) || (m.kind == NRB_MAT_PHONG && m.alpha_tex >= 0) ||
+                (m.kind == NRB_MAT_UV && !shape_has_uv(n.shape));
+    bool may_refract = (n.alpha != 1.0f) || (m.kind == NRB_MAT_PHONG && m.alpha_tex >= 0) ||
+                       (m.kind == NRB_MAT_UV && !shape_has_uv(n.shape));
+    is_cand[i] = cand ? 1 : 0;
+    any_refl = any_refl || (n.refl_mix != 0.0f);
+    any_refr = any_refr || may_refract;
+    NodeInfo ni{};
+    ni.material = n.material;
+    ni.refl_mix = n.refl_mix;
+    ni.refl_att = n.refl_atenuation;
+    ni.alpha = n.alpha;
+    ni.refr_coeff = (float)n.refr_coeff;
+    ni.flags = cand ? 1 : 0;
+    node_info[i] = ni;
+    if (n.shape == NRB_SHAPE_TRIMESH) {
+      if (n.first_index % 3 != 0 || n.tri_count == 0 || n.first_index + 3 * n.tri_count > d.n_indices || !d.indices ||
+          !d.positions)
+        return fail(NRB_ERR_INVALID_ARG, "node " + std::to_string(i) + ": trimesh index range invalid");
+      total_tris += n.tri_count;
+    } else {
+      Shape s{};
+      s.kind = n.shape;
+      s.node = (int)i;
+      s.solid = n.solid ? 1 : 0;
+      for (int k = 0; k < 3; ++k) s.p[k] = (float)n.param[k], s.trans[k] = (float)n.trans[k];
+      for (int k = 0; k < 9; ++k) s.rot[k] = (float)n.rot[k];
+      shape_of_node[i] = (int)shapes.size();
+      if (n.shape == NRB_SHAPE_PLANE) planes.push_back((int)shapes.size());
+      shapes.push_back(s);
+    }
+  }
+  if (total_tris >= (1ull << 28)) return fail(NRB_ERR_INVALID_ARG, "too many triangles (>= 2^28)");
+
+  // ---- triangles to world space (f64 transform, then f32) -------------------------------------
+  std::vector<Tri> tris_in(total_tris);
+  std::vector<TriUV> uvs_in(total_tris);
+  std::vector<Box> tri_box(total_tris);
+  std::vector<uint64_t> node_tri_begin(d.n_nodes, 0);
+  Box scene_box;
+  scene_box.reset();
+  {
+    uint64_t t_out = 0;
+    for (uint32_t i = 0; i < d.n_nodes; ++i) {
+      const NrbNodeDesc &n = d.nodes[i];
+      if (n.shape != NRB_SHAPE_TRIMESH) continue;
+      node_tri_begin[i] = t_out;
+      for (uint64_t t = 0; t < n.tri_count; ++t, ++t_out) {
+        double w[3][3];
+        TriUV uv{};
+        for (int k = 0; k < 3; ++k) {
+          uint64_t vi = (uint64_t)d.indices[n.first_index + 3 * t + k] + n.vertex_base;
+          if (vi >= d.n_vertices) return fail(NRB_ERR_INVALID_ARG, "node " + std::to_string(i) + ": vertex index out of range");
+          const float *p = d.positions + 3 * vi;
+          for (int r = 0; r < 3; ++r)
+            w[k][r] = n.rot[3 * r] * (double)p[0] + n.rot[3 * r + 1] * (double)p[1] + n.rot[3 * r + 2] * (double)p[2] + n.trans[r];
+          float uu = d.uvs ? d.uvs[2 * vi] : 0.0f, vv = d.uvs ? d.uvs[2 * vi + 1] : 0.0f;
+          if (k == 0) uv.u0 = uu, uv.v0 = vv;
+          if (k == 1) uv.u1 = uu, uv.v1 = vv;
+          if (k == 2) uv.u2 = uu, uv.v2 = vv;
+        }
+        Tri tr;
+        tr.t0 = make_float4((float)w[0][0], (float)w[0][1], (float)w[0][2], 0.0f);
+        int node_id = (int)i;
+        std::memcpy(&tr.t0.w, &node_id, 4);
+        tr.t1 = make_float4((float)(w[1][0] - w[0][0]), (float)(w[1][1] - w[0][1]), (float)(w[1][2] - w[0][2]), 0.0f);
+        tr.t2 = make_float4((float)(w[2][0] - w[0][0]), (float)(w[2][1] - w[0][1]), (float)(w[2][2] - w[0][2]), 0.0f);
+        tris_in[t_out] = tr;
+        uvs_in[t_out] = uv;
+        Box b;
+        b.reset();
+        float v0[3] = {tr.t0.x, tr.t0.y, tr.t0.z};
+        float v1[3] = {tr.t0.x + tr.t1.x, tr.t0.y + tr.t1.y, tr.t0.z + tr.t1.z};
+        float v2[3] = {tr.t0.x + tr.t2.x, tr.t0.y + tr.t2.y, tr.t0.z + tr.t2.z};
+        b.grow(v0), b.grow(v1), b.grow(v2);
+        for (int k = 0; k < 3; ++k) {
+          float wk[3] = {(float)w[k][0], (float)w[k][1], (float)w[k][2]};
+          b.grow(wk);
+        }
+        tri_box[t_out] = b;
+        scene_box.grow(b);
+      }
+    }
+  }
+  // shape boxes (bounding_volume(&transform), src/scene_node.rs:41), conservative
+  std::vector<Box> shape_box(shapes.size());
+  for (size_t si = 0; si < shapes.size(); ++si) {
+    const NrbNodeDesc &n = d.nodes[shapes[si].node];
+    Box b;
+    b.reset();
+    if (n.shape == NRB_SHAPE_PLANE) {
+      shape_box[si] = b;
+      continue;
+    }
+    double he[3];
+    switch (n.shape) {
+      case NRB_SHAPE_BALL:
+        he[0] = he[1] = he[2] = n.param[0];
+        break;
+      case NRB_SHAPE_CUBOID:
+        he[0] = n.param[0], he[1] = n.param[1], he[2] = n.param[2];
+        break;
+      case NRB_SHAPE_CAPSULE:
+        he[0] = n.param[1], he[1] = n.param[0] + n.param[1], he[2] = n.param[1];
+        break;
+      default:  // cylinder, cone
+        he[0] = n.param[1], he[1] = n.param[0], he[2] = n.param[1];
+        break;
+    }
+    for (int r = 0; r < 3; ++r) {
+      double e = n.shape == NRB_SHAPE_BALL
+                     ? he[0]
+                     : std::fabs(n.rot[3 * r]) * he[0] + std::fabs(n.rot[3 * r + 1]) * he[1] + std::fabs(n.rot[3 * r + 2]) * he[2];
+      b.lo[r] = (float)(n.trans[r] - e);
+      b.hi[r] = (float)(n.trans[r] + e);
+    }
+    shape_box[si] = b;
+    scene_box.grow(b);
+  }
+  float extent = 0.0f;
+  if (scene_box.valid())
+    for (int k = 0; k < 3; ++k) extent = std::max(extent, scene_box.hi[k] - scene_box.lo[k]);
+  for (auto &b : tri_box) pad_box(b, extent);
+  for (size_t si = 0; si < shapes.size(); ++si)
+    if (shape_box[si].valid()) pad_box(shape_box[si], extent);
+
+  // ---- BVH: opaque triangles | opaque shapes | one sub-root per transparent candidate | top level ----
+  BvhBuilder bb;
+  bb.nodes.reserve(total_tris / 2 + 16);
+  bb.tri_order.reserve(total_tris);
+  std::vector<BuildItem> opaque_items, top_items;
+  {
+    std::vector<BuildItem> items;
+    for (uint32_t i = 0; i < d.n_nodes; ++i) {
+      const NrbNodeDesc &n = d.nodes[i];
+      if (n.shape != NRB_SHAPE_TRIMESH || is_cand[i]) continue;
+      for (uint64_t t = 0; t < n.tri_count; ++t) items.push_back(BuildItem{tri_box[node_tri_begin[i] + t], (int)(node_tri_begin[i] + t)});
+    }
+    if (!items.empty()) {
+      Box rb;
+      int code = bb.build_triangles(items, &rb);
+      opaque_items.push_back(BuildItem{rb, code});
+    }
+  }
+  int depth_tri = bb.max_depth_seen;
+  std::vector<Candidate> candidates;
+  for (uint32_t i = 0; i < d.n_nodes; ++i) {
+    const NrbNodeDesc &n = d.nodes[i];
+    if (n.shape == NRB_SHAPE_PLANE) continue;
+    if (n.shape == NRB_SHAPE_TRIMESH) {
+      if (!is_cand[i]) continue;
+      std::vector<BuildItem> items;
+      for (uint64_t t = 0; t < n.tri_count; ++t) items.push_back(BuildItem{tri_box[node_tri_begin[i] + t], (int)(node_tri_begin[i] + t)});
+      Box rb;
+      bb.max_depth_seen = 0;
+      int code = bb.build_triangles(items, &rb);
+      depth_tri = std::max(depth_tri, bb.max_depth_seen);
+      Candidate c{};
+      for (int k = 0; k < 3; ++k) c.lo[k] = rb.lo[k], c.hi[k] = rb.hi[k];
+      c.root = code, c.node = (int)i;
+      candidates.push_back(c);
+      top_items.push_back(BuildItem{rb, code});
+    } else {
+      int si = shape_of_node[i];
+      int code = make_leaf((uint32_t)si, 1, true);
+      if (is_cand[i]) {
+        Candidate c{};
+        for (int k = 0; k < 3; ++k) c.lo[k] = shape_box[si].lo[k], c.hi[k] = shape_box[si].hi[k];
+        c.root = code, c.node = (int)i;
+        candidates.push_back(c);
+        top_items.push_back(BuildItem{shape_box[si], code});
+      } else {
+        opaque_items.push_back(BuildItem{shape_box[si], code});
+      }
+    }
+  }
+  int root_opaque = kEmpty, root_all = kEmpty;
+  int depth_mid = 0, depth_top = 0;
+  if (!opaque_items.empty()) {
+    Box rb;
+    bb.max_depth_seen = 0;
+    root_opaque = bb.build_payloads(opaque_items, &rb);
+    depth_mid = bb.max_depth_seen;
+    top_items.push_back(BuildItem{rb, root_opaque});
+  }
+  if (!top_items.empty()) {
+    Box rb;
+    bb.max_depth_seen = 0;
+    root_all = bb.build_payloads(top_items, &rb);
+    depth_top = bb.max_depth_seen;
+  }
+  // one stack slot per level at most (the far child of each two-hit node) + the sentinel
+  if (depth_tri + depth_mid + depth_top + 4 > kStackSize)
+    return fail(NRB_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+  relayout_bfs(bb.nodes, root_all, root_opaque, candidates);
+
+  // leaf-ordered triangle arrays
+  std::vector<Tri> tris(bb.tri_order.size());
+  std::vector<TriUV> tri_uvs(bb.tri_order.size());
+  for (size_t k = 0; k < bb.tri_order.size(); ++k) tris[k] = tris_in[bb.tri_order[k]], tri_uvs[k] = uvs_in[bb.tri_order[k]];
+  std::vector<Tri>().swap(tris_in);
+  std::vector<TriUV>().swap(uvs_in);
+
+  // ---- upload ---------------------------------------------------------------------------------
+  CU(upload(S.d_nodes, bb.nodes));
+  CU(upload(S.d_tris, tris));
+  CU(upload(S.d_tri_uvs, tri_uvs));
+  CU(upload(S.d_shapes, shapes));
+  CU(upload(S.d_node_info, node_info));
+  CU(upload(S.d_materials, materials));
+  CU(upload(S.d_textures, textures));
+  CU(upload(S.d_lights, lights));
+  CU(upload(S.d_planes, planes));
+  CU(upload(S.d_candidates, candidates));
+  {
+    size_t tb = std::max<size_t>(d.n_texels * 16, 16);
+    CU(S.d_texels.ensure(tb));
+    if (d.n_texels) CU(cudaMemcpy(S.d_texels.p, d.texels, d.n_texels * 16, cudaMemcpyHostToDevice));
+  }
+  SceneView &v = S.view;
+  v.nodes = S.d_nodes.as<BvhNode>();
+  v.tris = S.d_tris.as<Tri>();
+  v.tri_uvs = S.d_tri_uvs.as<TriUV>();
+  v.shapes = S.d_shapes.as<Shape>();
+  v.node_info = S.d_node_info.as<NodeInfo>();
+  v.materials = S.d_materials.as<Material>();
+  v.textures = S.d_textures.as<Texture>();
+  v.texels = S.d_texels.as<float4>();
+  v.lights = S.d_lights.as<Light>();
+  v.planes = S.d_planes.as<int>();
+  v.candidates = S.d_candidates.as<Candidate>();
+  v.root_all = root_all;
+  v.root_opaque = root_opaque;
+  v.n_planes = (int)planes.size();
+  v.n_candidates = (int)candidates.size();
+  v.n_lights = (int)lights.size();
+  v.shadow_samples = shadow_samples;
+  for (int k = 0; k < 3; ++k) v.background[k] = d.background[k];
+  S.has_shapes = !shapes.empty();
+  S.child_factor = (any_refl ? 1 : 0) + (any_refr ? 1 : 0);
+  S.n_bvh_nodes = bb.nodes.size();
+  S.n_tris = tris.size();
+  S.scene_bytes = bb.nodes.size() * sizeof(BvhNode) + tris.size() * (sizeof(Tri) + sizeof(TriUV)) +
+                  shapes.size() * sizeof(Shape) + d.n_texels * 16;
+  return NRB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene::render — wavefront driver
+// ---------------------------------------------------------------------------------------------
+int make_frame_params(const NrbCamera &cam, const NrbTileSet *tiles, FrameParams &fp) {
+  if (cam.ray_per_pixel == 0) return fail(NRB_ERR_INVALID_ARG, "ray_per_pixel must be > 0 (assert at src/scene.rs:37)");
+  if (cam.width == 0 || cam.height == 0) return fail(NRB_ERR_INVALID_ARG, "resolution must be non-zero");
+  uint64_t samples = (uint64_t)cam.width * cam.height * cam.ray_per_pixel;
+  if (samples >= (1ull << 32)) return fail(NRB_ERR_INVALID_ARG, "width*height*ray_per_pixel must be < 2^32");
+  std::memset(&fp, 0, sizeof(fp));
+  fp.width = cam.width, fp.height = cam.height, fp.spp = cam.ray_per_pixel;
+  fp.max_depth = cam.max_depth ? cam.max_depth : 64u;
+  fp.tiles_x = (cam.width + NRB_TILE - 1) / NRB_TILE;
+  fp.tiles_y = (cam.height + NRB_TILE - 1) / NRB_TILE;
+  uint32_t n_tiles = fp.tiles_x * fp.tiles_y;
+  if (tiles) {
+    if (tiles->stride == 0 || tiles->first >= tiles->stride) return fail(NRB_ERR_INVALID_ARG, "tile set: need first < stride, stride > 0");
+    fp.tile_first = tiles->first, fp.tile_stride = tiles->stride;
+    fp.n_local_tiles = tiles->first < n_tiles ? (n_tiles - tiles->first + tiles->stride - 1) / tiles->stride : 0;
+    fp.packed = 1;
+  } else {
+    fp.tile_first = 0, fp.tile_stride = 1, fp.n_local_tiles = n_tiles, fp.packed = 0;
+  }
+  fp.window = (float)cam.window_width;
+  fp.inv_w = 1.0f / (float)cam.width;
+  fp.inv_h = 1.0f / (float)cam.height;
+  // h = M * (x, y, -1, 1) = A x + B y + C (column-major M); direction ~ h.xyz - eye * h.w, evaluated
+  // in f64 here so the device adds three f32 vectors and never cancels against eye.
+  const double *M = cam.projection;
+  double A[4], B[4], Cc[4];
+  for (int r = 0; r < 4; ++r) A[r] = M[r], B[r] = M[4 + r], Cc[r] = -M[8 + r] + M[12 + r];
+  if (A[3] == 0.0 && B[3] == 0.0 && Cc[3] == 0.0)
+    return fail(NRB_ERR_INVALID_ARG, "projection maps the near plane to w == 0 (from_homogeneous().unwrap() panics: src/scene.rs:85)");
+  // scale so the vectors are O(1) in f32
+  double sc = 0.0;
+  for (int k = 0; k < 3; ++k) sc = std::max(sc, std::fabs(Cc[k] - cam.eye[k] * Cc[3]));
+  for (int k = 0; k < 3; ++k) sc = std::max(sc, std::max(std::fabs(A[k] - cam.eye[k] * A[3]), std::fabs(B[k] - cam.eye[k] * B[3])));
+  if (!(sc > 0.0) || !std::isfinite(sc)) return fail(NRB_ERR_INVALID_ARG, "degenerate projection matrix");
+  for (int k = 0; k < 3; ++k) {
+    fp.eye[k] = (float)cam.eye[k];
+    fp.dx[k] = (float)((A[k] - cam.eye[k] * A[3]) / sc);
+    fp.dy[k] = (float)((B[k] - cam.eye[k] * B[3]) / sc);
+    fp.d0[k] = (float)((Cc[k] - cam.eye[k] * Cc[3]) / sc);
+  }
+  double ws = std::max(std::fabs(A[3]), std::max(std::fabs(B[3]), std::fabs(Cc[3])));
+  fp.wx = (float)(A[3] / ws), fp.wy = (float)(B[3] / ws), fp.w0 = (float)(Cc[3] / ws);
+  fp.seed_lo = (uint32_t)cam.seed;
+  fp.seed_hi = (uint32_t)(cam.seed >> 32);
+  return NRB_OK;
+}
+
+cudaError_t ensure_ray_queue(NrbScene &S, int qi, uint32_t cap) {
+  if (cap <= S.q_cap[qi]) return cudaSuccess;
+  cap = std::max<uint32_t>(cap, 1024);
+  for (int c = 0; c < 3; ++c) {
+    cudaError_t e = S.d_q[qi][c].ensure((size_t)cap * 16);
+    if (e != cudaSuccess) return e;
+  }
+  S.q_cap[qi] = cap;
+  return cudaSuccess;
+}
+
+RayQueue ray_queue(NrbScene &S, int qi) {
+  return RayQueue{S.d_q[qi][0].as<float4>(), S.d_q[qi][1].as<float4>(), S.d_q[qi][2].as<float4>(), S.q_cap[qi]};
+}
+
+cudaEvent_t get_event(NrbScene &S, size_t &used) {
+  if (used == S.events.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    S.events.push_back(e);
+  }
+  return S.events[used++];
+}
+
+// Renders into S.d_accum and resolves to `d_out` (device; float rgb or u8 rgb).
+int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, float *d_out, uint8_t *d_out8,
+                  uint32_t *n_local_tiles, NrbStats *stats) {
+  CU(cudaSetDevice(S.device));
+  FrameParams fp;
+  int rc = make_frame_params(cam, tiles, fp);
+  if (rc) return rc;
+  if (n_local_tiles) *n_local_tiles = fp.n_local_tiles;
+  cudaStream_t st = S.stream;
+  const uint32_t n_acc = fp.packed ? fp.n_local_tiles * NRB_TILE * NRB_TILE : fp.width * fp.height;
+  CU(S.d_accum.ensure(std::max<size_t>((size_t)n_acc * 16, 16)));
+  float4 *accum = S.d_accum.as<float4>();
+  Counters *dc = S.d_counters.as<Counters>();
+  uint32_t launches = 0, waves = 0;
+  size_t ev_used = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_spans;
+
+  CU(cudaEventRecord(S.ev_begin, st));
+  CU(cudaMemsetAsync(accum, 0, (size_t)n_acc * 16, st));
+  CU(cudaMemsetAsync(dc, 0, sizeof(Counters), st));
+
+  const uint32_t per_tile = NRB_TILE * NRB_TILE * fp.spp;
+  const uint64_t total_slots = (uint64_t)fp.n_local_tiles * per_tile;
+  const uint64_t batch_slots_req = env_size("NRB_BATCH_SLOTS", 8u << 20);
+  const uint32_t tiles_per_batch = (uint32_t)std::max<uint64_t>(1, batch_slots_req / per_tile);
+  const uint64_t shadow_cap_req = env_size("NRB_SHADOW_CAP", 16u << 20);
+  const uint64_t mem_ceiling = env_size("NRB_QUEUE_BYTES", 64ull << 30);
+  const uint32_t S_total = (uint32_t)S.view.shadow_samples;
+  uint64_t primary = 0;
+
+  for (uint64_t tile_lo = 0; tile_lo < fp.n_local_tiles; tile_lo += tiles_per_batch) {
+    uint64_t tile_hi = std::min<uint64_t>(fp.n_local_tiles, tile_lo + tiles_per_batch);
+    uint32_t slot_lo = (uint32_t)(tile_lo * per_tile), slot_hi = (uint32_t)(tile_hi * per_tile);
+    (void)total_slots;
+    int cur = 0;
+    CU(ensure_ray_queue(S, 0, slot_hi - slot_lo));
+    CU(cudaMemsetAsync(&dc->n_rays[0], 0, 2 * sizeof(uint32_t), st));
+    launch_raygen(fp, slot_lo, slot_hi, ray_queue(S, 0), &dc->n_rays[0], st);
+    ++launches;
+    bool first_wave = true;
+    for (uint32_t depth = 0;; ++depth) {
+      CU(cudaMemcpyAsync(&S.h_counters->n_rays[cur], &dc->n_rays[cur], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      uint32_t n = S.h_counters->n_rays[cur];
+      if (first_wave) primary += n, first_wave = false;
+      if (n == 0) break;
+      ++waves;
+      // capacities for this wave
+      uint64_t next_need = (uint64_t)n * (uint64_t)S.child_factor;
+      if (next_need * 48 > mem_ceiling || next_need >= (1ull << 32))
+        return fail(NRB_ERR_QUEUE_OVERFLOW, "secondary-ray queue would exceed NRB_QUEUE_BYTES");
+      CU(ensure_ray_queue(S, 1 - cur, (uint32_t)next_need));
+      if (n > S.hits_cap) {
+        CU(S.d_hits.ensure((size_t)n * 16));
+        S.hits_cap = n;
+      }
+      uint32_t chunk = n;
+      if (S_total) {
+        uint64_t want = std::min<uint64_t>((uint64_t)n * S_total, std::max<uint64_t>(shadow_cap_req, S_total));
+        if (want > S.sq_cap) {
+          for (int c = 0; c < 3; ++c) CU(S.d_sq[c].ensure((size_t)want * 16));
+          S.sq_cap = (uint32_t)want;
+        }
+        chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n, S.sq_cap / S_total));
+      }
+      ShadowQueue sq{S.d_sq[0].as<float4>(), S.d_sq[1].as<float4>(), S.d_sq[2].as<float4>(), S.sq_cap};
+      CU(cudaMemsetAsync(&dc->n_rays[1 - cur], 0, sizeof(uint32_t), st));
+      CU(cudaMemsetAsync(&dc->fetch_closest, 0, sizeof(uint32_t), st));
+      // K2 closest hit
+      cudaEvent_t e0 = get_event(S, ev_used), e1 = get_event(S, ev_used);
+      CU(cudaEventRecord(e0, st));
+      launch_trace_closest(S.view, S.has_shapes, ray_queue(S, cur), S.d_hits.as<float4>(), &dc->n_rays[cur],
+                           &dc->fetch_closest, S.grid_closest, st);
+      CU(cudaEventRecord(e1, st));
+      trace_spans.emplace_back(e0, e1);
+      ++launches;
+      // K4 shade (+ K3 shadow) in chunks bounded by the shadow queue
+      for (uint32_t lo = 0; lo < n; lo += chunk) {
+        uint32_t hi = std::min<uint64_t>(n, (uint64_t)lo + chunk);
+        if (S_total) CU(cudaMemsetAsync(&dc->n_shadow, 0, sizeof(uint32_t), st));
+        launch_shade(S.view, S.has_shapes, fp, ray_queue(S, cur), S.d_hits.as<float4>(), lo, hi, ray_queue(S, 1 - cur),
+                     &dc->n_rays[1 - cur], sq, dc, accum, st);
+        ++launches;
+        if (S_total) {
+          CU(cudaMemsetAsync(&dc->fetch_shadow, 0, sizeof(uint32_t), st));
+          cudaEvent_t s0 = get_event(S, ev_used), s1 = get_event(S, ev_used);
+          CU(cudaEventRecord(s0, st));
+          launch_trace_shadow(S.view, S.has_shapes, sq, accum, &dc->n_shadow, &dc->fetch_shadow, S.grid_shadow, st);
+          CU(cudaEventRecord(s1, st));
+          trace_spans.emplace_back(s0, s1);
+          ++launches;
+        }
+      }
+      cur = 1 - cur;
+    }
+  }
+  if (d_out8)
+    launch_resolve_rgb8(accum, n_acc, fp.spp, d_out8, st);
+  else
+    launch_resolve(accum, n_acc, fp.spp, d_out, st);
+  ++launches;
+  CU(cudaEventRecord(S.ev_end, st));
+  CU(cudaMemcpyAsync(S.h_counters, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  if (S.h_counters->overflow) return fail(NRB_ERR_QUEUE_OVERFLOW, "a device queue overflowed (internal capacity bug)");
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->rays_primary = primary;
+    stats->rays_reflect = S.h_counters->rays_reflect;
+    stats->rays_refract = S.h_counters->rays_refract;
+    stats->rays_shadow = S.h_counters->rays_shadow;
+    stats->paths_truncated = S.h_counters->paths_truncated;
+    stats->waves = waves;
+    stats->kernel_launches = launches;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, S.ev_begin, S.ev_end);
+    stats->ms_device = ms;
+    float tr = 0.0f;
+    for (auto &sp : trace_spans) {
+      float t = 0.0f;
+      cudaEventElapsedTime(&t, sp.first, sp.second);
+      tr += t;
+    }
+    stats->ms_trace = tr;
+    stats->ms_shade = ms - tr;
+    stats->bvh_nodes = S.n_bvh_nodes;
+    stats->triangles = S.n_tris;
+    stats->scene_bytes = S.scene_bytes;
+  }
+  return NRB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// extern "C" entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *nrb_last_error(void) { return g_err.c_str(); }
+
+const char *nrb_version(void) { return "nrays_b200 abi1 sm_100a"; }
+
+int nrb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out) {
+  if (!desc || !out) return fail(NRB_ERR_INVALID_ARG, "desc/out is NULL");
+  if (desc->struct_size != sizeof(NrbSceneDesc) || desc->abi_version != NRB_ABI_VERSION)
+    return fail(NRB_ERR_INVALID_ARG, "NrbSceneDesc struct_size / abi_version mismatch");
+  int ndev = nrb_device_count();
+  if (ndev == 0) return fail(NRB_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(NRB_ERR_INVALID_ARG, "device index out of range");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(NRB_ERR_NO_DEVICE, "device is not sm_100 class (kernels are built for sm_100a only)");
+  std::unique_ptr<NrbScene> S(new NrbScene);
+  S->device = device;
+  S->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&S->ev_begin));
+  CU(cudaEventCreate(&S->ev_end));
+  CU(cudaHostAlloc((void **)&S->h_counters, sizeof(Counters), cudaHostAllocDefault));
+  CU(S->d_counters.ensure(sizeof(Counters)));
+  int rc = build_scene(*desc, *S);
+  if (rc) return rc;
+  S->grid_closest = S->sm_count * trace_blocks_per_sm(S->has_shapes, false);
+  S->grid_shadow = S->sm_count * trace_blocks_per_sm(S->has_shapes, true);
+  *out = S.release();
+  return NRB_OK;
+}
+
+void nrb_scene_destroy(NrbScene *scene) { delete scene; }
+
+int nrb_scene_set_background(NrbScene *scene, const float rgb[3]) {
+  if (!scene || !rgb) return fail(NRB_ERR_INVALID_ARG, "scene/rgb is NULL");
+  for (int k = 0; k < 3; ++k) scene->view.background[k] = rgb[k];
+  return NRB_OK;
+}
+
+int nrb_render_device(NrbScene *scene, const NrbCamera *camera, float *d_out_rgb, NrbStats *stats) {
+  if (!scene || !camera || !d_out_rgb) return fail(NRB_ERR_INVALID_ARG, "scene/camera/out is NULL");
+  return render_device(*scene, *camera, nullptr, d_out_rgb, nullptr, nullptr, stats);
+}
+
+int nrb_render(NrbScene *scene, const NrbCamera *camera, float *out_rgb, NrbStats *stats) {
+  if (!scene || !camera || !out_rgb) return fail(NRB_ERR_INVALID_ARG, "scene/camera/out is NULL");
+  CU(cudaSetDevice(scene->device));
+  size_t bytes = (size_t)camera->width * camera->height * 3 * sizeof(float);
+  CU(scene->d_out.ensure(std::max<size_t>(bytes, 16)));
+  int rc = render_device(*scene, *camera, nullptr, scene->d_out.as<float>(), nullptr, nullptr, stats);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out_rgb, scene->d_out.p, bytes, cudaMemcpyDeviceToHost, scene->stream));
+  CU(cudaStreamSynchronize(scene->stream));
+  return NRB_OK;
+}
+
+int nrb_render_rgb8(NrbScene *scene, const NrbCamera *camera, uint8_t *out_rgb8, NrbStats *stats) {
+  if (!scene || !camera || !out_rgb8) return fail(NRB_ERR_INVALID_ARG, "scene/camera/out is NULL");
+  CU(cudaSetDevice(scene->device));
+  size_t bytes = (size_t)camera->width * camera->height * 3;
+  CU(scene->d_out8.ensure(std::max<size_t>(bytes, 16)));
+  int rc = render_device(*scene, *camera, nullptr, nullptr, scene->d_out8.as<uint8_t>(), nullptr, stats);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out_rgb8, scene->d_out8.p, bytes, cudaMemcpyDeviceToHost, scene->stream));
+  CU(cudaStreamSynchronize(scene->stream));
+  return NRB_OK;
+}
+
+int nrb_render_tiles_device(NrbScene *scene, const NrbCamera *camera, const NrbTileSet *tiles, float *d_out_tiles,
+                            uint32_t *n_local_tiles, NrbStats *stats) {
+  if (!scene || !camera || !tiles || !d_out_tiles) return fail(NRB_ERR_INVALID_ARG, "scene/camera/tiles/out is NULL");
+  return render_device(*scene, *camera, tiles, d_out_tiles, nullptr, n_local_tiles, stats);
+}
+
+uint32_t nrb_tile_count(uint32_t width, uint32_t height) {
+  return ((width + NRB_TILE - 1) / NRB_TILE) * ((height + NRB_TILE - 1) / NRB_TILE);
+}
+
+uint32_t nrb_tile_count_local(uint32_t width, uint32_t height, const NrbTileSet *tiles) {
+  uint32_t n = nrb_tile_count(width, height);
+  if (!tiles || tiles->stride == 0 || tiles->first >= n) return tiles ? 0 : n;
+  return (n - tiles->first + tiles->stride - 1) / tiles->stride;
+}
+
+int nrb_untile_device(int device, const float *d_gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width,
+                      uint32_t height, float *d_out_rgb) {
+  if (!d_gathered || !d_out_rgb || n_ranks == 0) return fail(NRB_ERR_INVALID_ARG, "untile: bad arguments");
+  CU(cudaSetDevice(device));
+  launch_untile(d_gathered, n_ranks, tiles_per_rank, width, height, d_out_rgb, 0);
+  CU(cudaStreamSynchronize(0));
+  CU(cudaGetLastError());
+  return NRB_OK;
+}
+
+void *nrb_host_alloc(uint64_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    g_err = "cudaHostAlloc failed";
+    return nullptr;
+  }
+  return p;
+}
+
+void nrb_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

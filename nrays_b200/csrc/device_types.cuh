@@ -1,0 +1,170 @@
+// device_types.cuh — HBM data layout of the flattened scene and of the wavefront queues.
+//
+// Everything the kernels touch is f32 / u32 in 16-byte units so every access is a single 128-bit
+// load (LDG.E.128).  See DESIGN.md "Data layout in HBM" for the byte accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nrb {
+
+// ---- BVH ------------------------------------------------------------------------------------
+// One 64-byte node holds BOTH children's boxes (Aila-Laine layout), so one traversal step is four
+// 16-byte loads of one cache-line-aligned record and tests two boxes.
+//   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
+//   n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
+//   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
+//   n3 = (child0, child1, -, -) as int bits
+// Child code c:  c >= 0 -> inner node index;  c < 0 -> leaf, ~c = (first << 3) | ((count-1) << 1) | is_shape
+//   is_shape = 0: triangles [first, first+count) of the leaf-ordered triangle array (count <= 4)
+//   is_shape = 1: analytic shape `first` of the shape table (count == 1)
+struct __align__(16) BvhNode {
+  float4 n0, n1, n2;
+  int4 n3;
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
+
+constexpr int kEmpty = 0x7FFFFFFF;  // stack sentinel / "no root"
+constexpr int kMaxLeafTris = 4;
+constexpr int kStackSize = 64;
+
+__host__ __device__ inline int make_leaf(uint32_t first, uint32_t count, bool is_shape) {
+  return ~(int)((first << 3) | ((count - 1u) << 1) | (is_shape ? 1u : 0u));
+}
+
+// Triangle: 48 bytes, world space, edge form for the two-sided Ericson test.
+//   t0 = (v0.xyz, scene-node id as int bits), t1 = (e1.xyz, 0), t2 = (e2.xyz, 0);  e1 = v1-v0, e2 = v2-v0
+struct __align__(16) Tri {
+  float4 t0, t1, t2;
+};
+// Per-triangle vertex uvs, fetched only by the shade / shadow-filter code: 24 bytes.
+struct TriUV {
+  float u0, v0, u1, v1, u2, v2;
+};
+
+// Analytic SceneNode geometry (ball, cuboid, cylinder, capsule, cone, plane): 80 bytes.
+struct __align__(16) Shape {
+  int kind;   // NRB_SHAPE_*
+  int node;   // SceneNode index
+  int solid;  // SceneNode.solid
+  int _pad;
+  float p[4];    // shape parameters (see include/nrays_b200.h)
+  float rot[9];  // row-major rotation of the isometry
+  float trans[3];
+};
+static_assert(sizeof(Shape) == 80, "Shape must be 80 bytes");
+
+// SceneNode fields the shade code needs (src/scene_node.rs:8-19): 32 bytes.
+struct __align__(16) NodeInfo {
+  int material;
+  float refl_mix;
+  float refl_att;
+  float alpha;
+  float refr_coeff;
+  int flags;  // bit0: shadow-transparent candidate (own BVH root)
+  int _pad[2];
+};
+
+struct __align__(16) Material {  // 64 bytes
+  int kind;
+  float ambient[3];
+  float diffuse[3];
+  float specular[3];
+  float shininess;
+  int tex;
+  int alpha_tex;
+  int _pad[3];
+};
+static_assert(sizeof(Material) == 64, "Material layout");
+
+struct Texture {
+  uint32_t w, h;
+  int interp, overflow;
+  uint32_t offset;  // texel offset into the RGBA32F pool
+  uint32_t avail;   // texels from offset to the end of the pool
+};
+
+struct Light {
+  float pos[3];
+  float radius;
+  float color[3];
+  uint32_t racsample;
+};
+
+// A shadow-transparent candidate SceneNode: closest hit per node decides filter vs occlusion
+// (src/scene.rs:304-339).
+struct Candidate {
+  float lo[3], hi[3];
+  int root;  // child code of its own sub-tree (triangle mesh) or shape leaf
+  int node;  // SceneNode index
+};
+
+struct SceneView {
+  const BvhNode *nodes;
+  const Tri *tris;
+  const TriUV *tri_uvs;
+  const Shape *shapes;
+  const NodeInfo *node_info;
+  const Material *materials;
+  const Texture *textures;
+  const float4 *texels;
+  const Light *lights;
+  const int *planes;            // shape indices of all planes (always tested, never in the BVH)
+  const Candidate *candidates;  // shadow-transparent candidates that are not planes
+  int root_all;                 // closest-hit entry (kEmpty if the scene has only planes)
+  int root_opaque;              // any-hit entry for shadow rays (kEmpty if none)
+  int n_planes;
+  int n_candidates;
+  int n_lights;
+  int shadow_samples;  // sum over lights of racsample^2
+  float background[3];
+};
+
+// ---- wavefront queues (SoA of 16-byte columns) -------------------------------------------------
+// Ray record, 48 bytes in three columns:
+//   a = (o.x, o.y, o.z, d.x)   b = (d.y, d.z, weight, energy)   c = (refr, gid, path, depth) [gid/path/depth as uint bits]
+// gid = pixel_index * spp + sample (global, independent of sharding) -> RNG counter + accumulation address.
+struct RayQueue {
+  float4 *a, *b, *c;
+  uint32_t capacity;
+};
+// Hit record, 16 bytes: (t, prim, u, v).  prim (uint bits): triangle index in leaf order, or
+// 0x80000000 | shape index, or kMiss.
+constexpr uint32_t kMiss = 0xFFFFFFFFu;
+constexpr uint32_t kShapeBit = 0x80000000u;
+// Shadow ray record, 48 bytes in three columns:
+//   a = (o.xyz, tmax)   b = (d.xyz, pixel address as uint bits)   c = (contribution rgb, -)
+struct ShadowQueue {
+  float4 *a, *b, *c;
+  uint32_t capacity;
+};
+
+// Device counters block (one per scene handle)
+struct Counters {
+  uint32_t n_rays[2];      // ray queue tails (ping-pong)
+  uint32_t n_shadow;       // shadow queue tail
+  uint32_t fetch_closest;  // persistent-kernel work counters
+  uint32_t fetch_shadow;
+  uint32_t overflow;       // set if any queue append was dropped
+  uint32_t _pad[2];
+  unsigned long long rays_reflect, rays_refract, rays_shadow, paths_truncated;
+};
+
+// Per-frame constants
+struct FrameParams {
+  uint32_t width, height, spp, max_depth;
+  uint32_t tiles_x, tiles_y;
+  uint32_t tile_first, tile_stride;  // tile set rendered by this call
+  uint32_t n_local_tiles;
+  uint32_t packed;  // 0: accumulate into a row-major image; 1: into packed tiles [n_local][16][16]
+  float window;
+  float inv_w, inv_h;
+  float eye[3];
+  // primary direction = normalize(dx * ndc.x + dy * ndc.y + d0) (host-derived in f64 from the
+  // inverse view-projection so the device never subtracts eye from a near-plane point)
+  float dx[3], dy[3], d0[3];
+  float wx, wy, w0;  // homogeneous w = wx * ndc.x + wy * ndc.y + w0; the direction flips when w < 0
+  uint32_t seed_lo, seed_hi;
+};
+
+}  // namespace nrb

@@ -1,0 +1,660 @@
+// kernels.cu — the sm_100a kernels of the nrays render path (wavefront formulation).
+//
+//   K1 raygen_kernel          src/scene.rs:67-89      primary rays (jitter + unproject) -> ray queue
+//   K2 trace_closest_kernel   src/scene.rs:163-166, 262-283 + ncollide3d BVT/RayCast
+//   K3 trace_shadow_kernel    src/scene.rs:147-161, 285-339 (Scene::intersects_ray + transparent filter)
+//   K4 shade_kernel           src/scene.rs:168-252, src/phong_material.rs:72-151, src/light.rs:56-63,
+//                             src/texture2d.rs:207-256, normal/uv materials
+//   K5 resolve_kernel         src/scene.rs:94 (tot_c / spp) [+ src/image.rs:64-77 RGB8 quantisation]
+//   K6 untile_kernel          (multi-GPU) packed 16x16 tiles -> row-major image
+//
+// The reference recursion `trace` is linear in its reflection / refraction children, so each ray
+// carries a scalar weight and every hit / miss / unoccluded light sample adds its weighted colour
+// straight into the pixel accumulator (SURVEY §7 "Hard parts").
+#include "device_math.cuh"
+#include "kernels.h"
+
+namespace nrb {
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+NRB_DI uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// Warp-aggregated queue append: one atomicAdd per warp, dense slots in lane order.
+NRB_DI uint32_t warp_append(uint32_t *tail, bool want) {
+  uint32_t mask = __ballot_sync(0xFFFFFFFFu, want);
+  if (mask == 0) return 0;
+  uint32_t leader = __ffs(mask) - 1;
+  uint32_t base = 0;
+  if (lane_id() == leader) base = atomicAdd(tail, __popc(mask));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  return base + __popc(mask & ((1u << lane_id()) - 1u));
+}
+
+// Warp-aggregated append of a variable number of entries per lane (exclusive scan by shuffles);
+// the warp total is also added to `count_ctr` (ray statistics).
+NRB_DI uint32_t warp_append_n(uint32_t *tail, uint32_t n, unsigned long long *count_ctr) {
+  uint32_t incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if ((int)lane_id() >= o) incl += v;
+  }
+  uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  uint32_t base = 0;
+  if (total == 0) return 0;
+  if (lane_id() == 0) {
+    base = atomicAdd(tail, total);
+    atomicAdd(count_ctr, (unsigned long long)total);
+  }
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  return base + incl - n;
+}
+
+NRB_DI void count_warp(unsigned long long *ctr, bool pred) {
+  uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
+  if (mask && lane_id() == (uint32_t)(__ffs(mask) - 1)) atomicAdd(ctr, (unsigned long long)__popc(mask));
+}
+
+// 8-bit Morton decode (4 bits x, 4 bits y) for the in-tile pixel order
+NRB_DI uint32_t compact4(uint32_t v) {
+  v &= 0x55u;
+  v = (v | (v >> 1)) & 0x33u;
+  v = (v | (v >> 2)) & 0x0Fu;
+  return v;
+}
+
+NRB_DI uint32_t accum_index(const FrameParams &fp, uint32_t ipt) {
+  if (!fp.packed) return ipt;
+  uint32_t y = ipt / fp.width, x = ipt - y * fp.width;
+  uint32_t tile = (y / NRB_TILE) * fp.tiles_x + (x / NRB_TILE);
+  uint32_t lt = (tile - fp.tile_first) / fp.tile_stride;
+  return lt * (NRB_TILE * NRB_TILE) + (y % NRB_TILE) * NRB_TILE + (x % NRB_TILE);
+}
+
+NRB_DI void accum_add(float4 *accum, uint32_t idx, V3 c) {
+  if (c.x == 0.0f && c.y == 0.0f && c.z == 0.0f) return;
+  atomicAdd(&accum[idx], make_float4(c.x, c.y, c.z, 0.0f));  // one 128-bit RED (sm_90+)
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 — primary rays (src/scene.rs:67-89)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) raygen_kernel(FrameParams fp, uint32_t slot_begin, uint32_t slot_end,
+                                                     RayQueue q, uint32_t *tail) {
+  uint32_t slot = slot_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = slot < slot_end;
+  uint32_t per_tile = NRB_TILE * NRB_TILE * fp.spp;
+  uint32_t lt = slot / per_tile, r = slot - lt * per_tile;
+  uint32_t p = r / fp.spp, s = r - p * fp.spp;
+  uint32_t tile = fp.tile_first + lt * fp.tile_stride;
+  uint32_t ty = tile / fp.tiles_x, tx = tile - ty * fp.tiles_x;
+  uint32_t x = tx * NRB_TILE + compact4(p), y = ty * NRB_TILE + compact4(p >> 1);
+  valid = valid && x < fp.width && y < fp.height;
+  uint32_t ipt = y * fp.width + x;
+  float jx = 0.0f, jy = 0.0f;
+  if (valid && fp.window != 0.0f) {
+    uint32_t rnd[4];
+    philox4x32_10(ipt, s, 0u, 0u, fp.seed_lo, fp.seed_hi ^ kStreamPrimary, rnd);
+    jx = (u24(rnd[0]) - 0.5f) * fp.window;
+    jy = (u24(rnd[1]) - 0.5f) * fp.window;
+  }
+  float fx = (float)x + jx, fy = (float)y + jy;
+  float ndx = (fx * fp.inv_w - 0.5f) * 2.0f;
+  float ndy = -(fy * fp.inv_h - 0.5f) * 2.0f;
+  V3 d = mk(fp.dx[0], fp.dx[1], fp.dx[2]) * ndx + mk(fp.dy[0], fp.dy[1], fp.dy[2]) * ndy + mk(fp.d0[0], fp.d0[1], fp.d0[2]);
+  float w = fp.wx * ndx + fp.wy * ndy + fp.w0;
+  d = normalize(d);
+  if (w < 0.0f) d = -d;
+  uint32_t idx = warp_append(tail, valid);
+  if (valid && idx < q.capacity) {
+    q.a[idx] = make_float4(fp.eye[0], fp.eye[1], fp.eye[2], d.x);
+    q.b[idx] = make_float4(d.y, d.z, 1.0f /*weight*/, 1.0f /*energy*/);
+    q.c[idx] = make_float4(1.0f /*refr*/, __uint_as_float(ipt * fp.spp + s), __uint_as_float(1u) /*path*/,
+                           __uint_as_float(0u) /*depth*/);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BVH traversal (per-lane while-while with an explicit stack)
+// ---------------------------------------------------------------------------------------------
+struct Hit {
+  float t;
+  uint32_t prim;
+  float u, v;
+};
+
+// ANY = true: return at the first hit with toi <= tmax (shadow rays vs opaque geometry).
+// ANY = false: closest hit with toi < tmax (strict, best_first_search keeps the first of equals).
+template <bool HAS_SHAPES, bool ANY>
+NRB_DI bool traverse(const SceneView &sc, int root, V3 o, V3 d, float tmax, Hit &hit) {
+  int stack[kStackSize];
+  int sp = 0;
+  stack[0] = kEmpty;
+  int node = root;
+  bool found = false;
+  const float ooeps = 1.0e-24f;
+  float idx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+  float idy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+  float idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+  float oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;
+  float tbest = tmax;
+
+  while (node != kEmpty) {
+    // ---- inner nodes: one 64-byte record = both children's boxes ----
+    while ((unsigned)node < (unsigned)kEmpty) {
+      const float4 *np = reinterpret_cast<const float4 *>(sc.nodes + node);
+      float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+      int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
+      float c0lox = fmaf(n0.x, idx, -oodx), c0hix = fmaf(n0.y, idx, -oodx);
+      float c0loy = fmaf(n0.z, idy, -oody), c0hiy = fmaf(n0.w, idy, -oody);
+      float c0loz = fmaf(n2.x, idz, -oodz), c0hiz = fmaf(n2.y, idz, -oodz);
+      float c1lox = fmaf(n1.x, idx, -oodx), c1hix = fmaf(n1.y, idx, -oodx);
+      float c1loy = fmaf(n1.z, idy, -oody), c1hiy = fmaf(n1.w, idy, -oody);
+      float c1loz = fmaf(n2.z, idz, -oodz), c1hiz = fmaf(n2.w, idz, -oodz);
+      float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
+      float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tbest));
+      float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
+      float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tbest));
+      bool h0 = c0max >= c0min, h1 = c1max >= c1min;
+      if (!h0 && !h1) {
+        node = stack[sp--];
+      } else {
+        node = h0 ? ch.x : ch.y;
+        if (h0 && h1) {
+          int far = ch.y;
+          if (c1min < c0min) {
+            far = ch.x;
+            node = ch.y;
+          }
+          stack[++sp] = far;
+        }
+      }
+    }
+    // ---- leaves ----
+    while (node < 0) {
+      uint32_t code = (uint32_t)~node;
+      uint32_t first = code >> 3, cnt = ((code >> 1) & 3u) + 1u;
+      if (HAS_SHAPES && (code & 1u)) {
+        Inter it;
+        if (cast_shape(sc.shapes[first], o, d, it) && (ANY ? it.toi <= tbest : it.toi < tbest)) {
+          tbest = it.toi;
+          hit.t = it.toi, hit.prim = kShapeBit | first, hit.u = it.u, hit.v = it.v;
+          found = true;
+          if (ANY) return true;
+        }
+      } else {
+        const float4 *tp = reinterpret_cast<const float4 *>(sc.tris + first);
+        for (uint32_t k = 0; k < cnt; ++k) {
+          float4 t0 = __ldg(tp + 3 * k), t1 = __ldg(tp + 3 * k + 1), t2 = __ldg(tp + 3 * k + 2);
+          float toi, bv, bw;
+          if (cast_tri<ANY>(mk(t0.x, t0.y, t0.z), mk(t1.x, t1.y, t1.z), mk(t2.x, t2.y, t2.z), o, d, tbest, toi, bv, bw)) {
+            tbest = toi;
+            hit.t = toi, hit.prim = first + k, hit.u = bv, hit.v = bw;
+            found = true;
+            if (ANY) return true;
+          }
+        }
+      }
+      node = stack[sp--];
+    }
+  }
+  return found;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 — closest hit (Scene::trace's best_first_search, src/scene.rs:164-166)
+// Persistent warps: each warp pulls packets of 32 rays from the queue with one atomic.
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_SHAPES>
+__global__ void __launch_bounds__(kTraceBlock) trace_closest_kernel(SceneView sc, RayQueue q, float4 *hits,
+                                                                   const uint32_t *count_ptr, uint32_t *fetch) {
+  const uint32_t count = *count_ptr;
+  while (true) {
+    uint32_t base = 0;
+    if (lane_id() == 0) base = atomicAdd(fetch, 32u);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= count) break;
+    uint32_t i = base + lane_id();
+    if (i < count) {
+      float4 a = q.a[i], b = q.b[i];
+      V3 o = mk(a.x, a.y, a.z), d = mk(a.w, b.x, b.y);
+      Hit hit;
+      hit.t = 3.402823466e+38f, hit.prim = kMiss, hit.u = hit.v = 0.0f;
+      if (HAS_SHAPES) {
+        // planes have infinite AABBs: always tested, never in the BVH
+        for (int p = 0; p < sc.n_planes; ++p) {
+          int si = sc.planes[p];
+          Inter it;
+          if (cast_shape(sc.shapes[si], o, d, it) && it.toi < hit.t) {
+            hit.t = it.toi, hit.prim = kShapeBit | (uint32_t)si, hit.u = 0.0f, hit.v = 0.0f;
+          }
+        }
+      }
+      if (sc.root_all != kEmpty) traverse<HAS_SHAPES, false>(sc, sc.root_all, o, d, hit.t, hit);
+      hits[i] = make_float4(hit.t, __uint_as_float(hit.prim), hit.u, hit.v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// surface reconstruction shared by shade and the shadow filter
+// ---------------------------------------------------------------------------------------------
+struct Surface {
+  V3 n;
+  float u, v;
+  bool has_uv;
+  int node;
+};
+
+template <bool HAS_SHAPES>
+NRB_DI void reconstruct(const SceneView &sc, V3 o, V3 d, uint32_t prim, float bu, float bv, Surface &s) {
+  if (HAS_SHAPES && (prim & kShapeBit)) {
+    const Shape &sh = sc.shapes[prim & ~kShapeBit];
+    Inter it;
+    it.n = mk(0, 0, 0), it.u = it.v = 0.0f, it.has_uv = false;
+    cast_shape(sh, o, d, it);
+    s.n = it.n, s.u = it.u, s.v = it.v, s.has_uv = it.has_uv, s.node = sh.node;
+    return;
+  }
+  const float4 *tp = reinterpret_cast<const float4 *>(sc.tris + prim);
+  float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+  V3 e1 = mk(t1.x, t1.y, t1.z), e2 = mk(t2.x, t2.y, t2.z);
+  V3 n = cross(e1, e2);
+  float t = dot(o - mk(t0.x, t0.y, t0.z), n);  // same expression as cast_tri: normal faces the ray origin
+  V3 nn = normalize(n);
+  s.n = t < 0.0f ? -nn : nn;
+  const TriUV uv = sc.tri_uvs[prim];
+  float bw0 = -bu - bv + 1.0f;
+  s.u = uv.u0 * bw0 + uv.u1 * bu + uv.u2 * bv;
+  s.v = uv.v0 * bw0 + uv.v1 * bu + uv.v2 * bv;
+  s.has_uv = true;
+  s.node = __float_as_int(t0.w);
+}
+
+// Material::ambiant (src/phong_material.rs:39-70, normal_material.rs:7-15, uv_material.rs:8-21)
+NRB_DI float4 mat_ambiant(const SceneView &sc, const Material &m, const Surface &s) {
+  if (m.kind == NRB_MAT_NORMAL)
+    return make_float4((1.0f + s.n.x) / 2.0f, (1.0f + s.n.y) / 2.0f, (1.0f + s.n.z) / 2.0f, 1.0f);
+  if (m.kind == NRB_MAT_UV) return s.has_uv ? make_float4(s.u, s.v, 0.0f, 1.0f) : make_float4(0, 0, 0, 0);
+  if (s.has_uv) {
+    float4 tc = make_float4(1, 1, 1, 1);
+    if (m.tex >= 0) {
+      tc = tex_sample(sc, m.tex, s.u, s.v);
+      tc.w = 1.0f;
+    }
+    if (m.alpha_tex >= 0) tc.w = tex_sample(sc, m.alpha_tex, s.u, s.v).w;
+    return make_float4(m.ambient[0] * tc.x, m.ambient[1] * tc.y, m.ambient[2] * tc.z, tc.w);
+  }
+  return make_float4(m.ambient[0], m.ambient[1], m.ambient[2], 1.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 — shadow rays (Scene::intersects_ray, src/scene.rs:147-161 + :285-339)
+// Outcome: any SceneNode whose closest hit is opaque with toi <= maxtoi => shadowed;
+// otherwise filter = product over nodes whose closest hit within maxtoi is transparent.
+// Opaque-certain geometry lives under root_opaque (any-hit is exact for it); every node that can be
+// transparent has its own sub-root and is resolved by its own closest hit.
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_SHAPES>
+NRB_DI bool shadow_candidate(const SceneView &sc, int root, int node_id, V3 o, V3 d, float tmax, V3 &filter) {
+  Hit h;
+  h.t = 0, h.prim = kMiss, h.u = h.v = 0;
+  // closest hit of this node with toi <= tmax
+  if (!traverse<HAS_SHAPES, false>(sc, root, o, d, nextafterf(tmax, 3.402823466e+38f), h)) return false;
+  Surface s;
+  reconstruct<HAS_SHAPES>(sc, o, d, h.prim, h.u, h.v, s);
+  const NodeInfo ni = sc.node_info[node_id];
+  float4 c = mat_ambiant(sc, sc.materials[ni.material], s);
+  float alpha = c.w * ni.alpha;
+  if (alpha < 1.0f) {
+    float k = 1.0f - alpha;
+    filter = mk(filter.x * c.x * k, filter.y * c.y * k, filter.z * c.z * k);
+    return false;
+  }
+  return true;  // opaque
+}
+
+template <bool HAS_SHAPES>
+__global__ void __launch_bounds__(kTraceBlock) trace_shadow_kernel(SceneView sc, ShadowQueue q, float4 *accum,
+                                                                  const uint32_t *count_ptr, uint32_t *fetch) {
+  const uint32_t count = min(*count_ptr, q.capacity);
+  while (true) {
+    uint32_t base = 0;
+    if (lane_id() == 0) base = atomicAdd(fetch, 32u);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= count) break;
+    uint32_t i = base + lane_id();
+    if (i < count) {
+      float4 a = q.a[i], b = q.b[i];
+      V3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
+      float tmax = a.w;
+      bool occluded = false;
+      V3 filter = mk(1, 1, 1);
+      if (HAS_SHAPES) {
+        for (int p = 0; p < sc.n_planes && !occluded; ++p) {
+          int si = sc.planes[p];
+          const Shape &sh = sc.shapes[si];
+          if (sc.node_info[sh.node].flags & 1) {
+            // transparent candidate plane: its (only) hit filters or occludes
+            Inter it;
+            if (cast_shape(sh, o, d, it) && it.toi <= tmax) {
+              Surface s;
+              s.n = it.n, s.u = it.u, s.v = it.v, s.has_uv = it.has_uv, s.node = sh.node;
+              const NodeInfo ni = sc.node_info[sh.node];
+              float4 c = mat_ambiant(sc, sc.materials[ni.material], s);
+              float alpha = c.w * ni.alpha;
+              if (alpha < 1.0f) {
+                float k = 1.0f - alpha;
+                filter = mk(filter.x * c.x * k, filter.y * c.y * k, filter.z * c.z * k);
+              } else {
+                occluded = true;
+              }
+            }
+          } else {
+            Inter it;
+            if (cast_shape(sh, o, d, it) && it.toi <= tmax) occluded = true;
+          }
+        }
+      }
+      if (!occluded && sc.root_opaque != kEmpty) {
+        Hit h;
+        occluded = traverse<HAS_SHAPES, true>(sc, sc.root_opaque, o, d, tmax, h);
+      }
+      if (!occluded) {
+        for (int c = 0; c < sc.n_candidates && !occluded; ++c) {
+          const Candidate cd = sc.candidates[c];
+          // slab test against the candidate's box (bv cost), origin-inside counts as hit
+          float t0 = 0.0f, t1 = tmax;
+          bool miss = false;
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) {
+            float oi = comp(o, ax), di = comp(d, ax);
+            if (di == 0.0f) {
+              if (oi < cd.lo[ax] || oi > cd.hi[ax]) miss = true;
+            } else {
+              float inv = 1.0f / di;
+              float ta = (cd.lo[ax] - oi) * inv, tb = (cd.hi[ax] - oi) * inv;
+              t0 = fmaxf(t0, fminf(ta, tb));
+              t1 = fminf(t1, fmaxf(ta, tb));
+            }
+          }
+          if (miss || t0 > t1) continue;
+          occluded = shadow_candidate<HAS_SHAPES>(sc, cd.root, cd.node, o, d, tmax, filter);
+        }
+      }
+      if (!occluded) {
+        float4 cc = q.c[i];
+        accum_add(accum, __float_as_uint(b.w), mk(cc.x * filter.x, cc.y * filter.y, cc.z * filter.z));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4 — shade + secondary-ray generation (Scene::trace body after the cast, src/scene.rs:168-192)
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_SHAPES>
+__global__ void __launch_bounds__(kShadeBlock) shade_kernel(SceneView sc, FrameParams fp, RayQueue qin,
+                                                           const float4 *hits, uint32_t lo, uint32_t hi,
+                                                           RayQueue qout, uint32_t *tail_out, ShadowQueue sq,
+                                                           Counters *ctr, float4 *accum) {
+  uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = i < hi;
+  float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra, h = ra;
+  if (active) {
+    ra = qin.a[i], rb = qin.b[i], rc = qin.c[i];
+    h = hits[i];
+  }
+  V3 o = mk(ra.x, ra.y, ra.z), d = mk(ra.w, rb.x, rb.y);
+  float weight = rb.z, energy = rb.w, refr = rc.x;
+  uint32_t gid = __float_as_uint(rc.y), path = __float_as_uint(rc.z), depth = __float_as_uint(rc.w);
+  uint32_t prim = __float_as_uint(h.y);
+  uint32_t ipt = gid / fp.spp, smp = gid - ipt * fp.spp;
+  uint32_t pix = active ? accum_index(fp, ipt) : 0u;
+
+  bool is_hit = active && prim != kMiss;
+  if (active && !is_hit) {
+    // miss -> background (src/scene.rs:169)
+    accum_add(accum, pix, mk(sc.background[0], sc.background[1], sc.background[2]) * weight);
+  }
+
+  // ---- hit: reconstruct the intersection, evaluate the material --------------------------------
+  Surface s;
+  s.n = mk(0, 0, 1), s.u = s.v = 0.0f, s.has_uv = false, s.node = 0;
+  V3 pt = mk(0, 0, 0);
+  NodeInfo ni;
+  ni.material = 0, ni.refl_mix = 0, ni.refl_att = 0, ni.alpha = 1, ni.refr_coeff = 1, ni.flags = 0;
+  Material m;
+  m.kind = NRB_MAT_NORMAL;
+  float4 tex_color = make_float4(1, 1, 1, 1);
+  float obj_w = 1.0f;
+  V3 obj_rgb = mk(0, 0, 0);
+  bool phong = false;
+  if (is_hit) {
+    reconstruct<HAS_SHAPES>(sc, o, d, prim, h.z, h.w, s);
+    pt = o + d * h.x;
+    ni = sc.node_info[s.node];
+    m = sc.materials[ni.material];
+    if (m.kind == NRB_MAT_PHONG) {
+      // PhongMaterial::compute, ambient part (src/phong_material.rs:85-103)
+      phong = true;
+      if (s.has_uv && m.tex >= 0) tex_color = tex_sample(sc, m.tex, s.u, s.v);
+      if (s.has_uv && m.alpha_tex >= 0) obj_w = tex_sample(sc, m.alpha_tex, s.u, s.v).w;
+      obj_rgb = mk(m.ambient[0] * tex_color.x, m.ambient[1] * tex_color.y, m.ambient[2] * tex_color.z);
+    } else {
+      float4 c = mat_ambiant(sc, m, s);  // Material::compute default (src/material.rs:8-16)
+      obj_rgb = mk(c.x, c.y, c.z);
+      obj_w = c.w;
+    }
+  }
+  // combine weights (src/scene.rs:178-190): out = alpha==1 ? col : col*alpha + refr*(1-alpha),
+  // col = obj*(1-mix) + refl*mix
+  float alpha = obj_w * ni.alpha;
+  float a1 = (alpha == 1.0f) ? 1.0f : alpha;
+  float w_obj = weight * a1 * (1.0f - ni.refl_mix);
+  if (is_hit) accum_add(accum, pix, obj_rgb * w_obj);
+
+  // ---- light samples -> shadow rays (src/phong_material.rs:106-147, src/light.rs:56-63) --------
+  uint32_t n_sh = (is_hit && phong) ? (uint32_t)sc.shadow_samples : 0u;
+  uint32_t sbase = warp_append_n(&ctr->n_shadow, n_sh, &ctr->rays_shadow);
+  if (n_sh) {
+    uint32_t k_out = 0;
+    for (int li = 0; li < sc.n_lights; ++li) {
+      const Light L = sc.lights[li];
+      uint32_t ns = L.racsample * L.racsample;
+      float inv_ns = 1.0f / (float)ns;
+      for (uint32_t k = 0; k < ns; ++k, ++k_out) {
+        V3 pos = mk(L.pos[0], L.pos[1], L.pos[2]);
+        if (L.radius != 0.0f) {
+          uint32_t rnd[4];
+          philox4x32_10(ipt, smp, path, ((uint32_t)li << 16) | (k & 0xFFFFu), fp.seed_lo, fp.seed_hi ^ kStreamLight, rnd);
+          pos = pos + mk(u24(rnd[0]), u24(rnd[1]), u24(rnd[2])) * L.radius;
+        }
+        V3 ldir = pos - pt;
+        float len = sqrtf(dot(ldir, ldir));
+        ldir = ldir * (1.0f / len);
+        float dist = len - 0.001f;
+        float ndl = dot(ldir, s.n);
+        float dcoeff = fmaxf(ndl, 0.0f);
+        V3 diffuse = mk(m.diffuse[0] * tex_color.x, m.diffuse[1] * tex_color.y, m.diffuse[2] * tex_color.z) * dcoeff;
+        V3 rl = normalize(-ldir + s.n * (2.0f * ndl));
+        float scoeff = -dot(rl, d);
+        V3 c = diffuse;
+        if (scoeff > 0.0f) {
+          float sp = powf(scoeff, m.shininess);
+          c = c + mk(m.specular[0], m.specular[1], m.specular[2]) * sp;
+        }
+        c = cmul(mk(L.color[0], L.color[1], L.color[2]), c) * (inv_ns * w_obj);
+        uint32_t si = sbase + k_out;
+        if (si < sq.capacity) {
+          V3 so = pt + ldir * 0.001f;
+          sq.a[si] = make_float4(so.x, so.y, so.z, dist);
+          sq.b[si] = make_float4(ldir.x, ldir.y, ldir.z, __uint_as_float(pix));
+          sq.c[si] = make_float4(c.x, c.y, c.z, 0.0f);
+        } else {
+          ctr->overflow = 1u;
+        }
+      }
+    }
+  }
+
+  // ---- reflection (Scene::trace_reflection, src/scene.rs:196-218) ------------------------------
+  bool want_refl = is_hit && ni.refl_mix != 0.0f && energy > 0.1f;
+  bool trunc_refl = want_refl && (depth + 1u >= fp.max_depth);
+  want_refl = want_refl && !trunc_refl;
+  // ---- refraction (Scene::trace_refraction, src/scene.rs:221-252) ------------------------------
+  bool want_refr = is_hit && alpha != 1.0f;
+  bool trunc_refr = want_refr && (depth + 1u >= fp.max_depth);
+  want_refr = want_refr && !trunc_refr;
+  count_warp(&ctr->paths_truncated, trunc_refl);
+  count_warp(&ctr->paths_truncated, trunc_refr);
+  count_warp(&ctr->rays_reflect, want_refl);
+  count_warp(&ctr->rays_refract, want_refr);
+
+  uint32_t ri = warp_append(tail_out, want_refl);
+  if (want_refl) {
+    if (ri < qout.capacity) {
+      float dn = dot(d, s.n);
+      V3 rdir = d - s.n * (2.0f * dn);
+      V3 ro = pt + rdir * 0.001f;
+      qout.a[ri] = make_float4(ro.x, ro.y, ro.z, rdir.x);
+      qout.b[ri] = make_float4(rdir.y, rdir.z, weight * a1 * ni.refl_mix, energy - ni.refl_att);
+      qout.c[ri] = make_float4(refr, __uint_as_float(gid), __uint_as_float(path * 2u), __uint_as_float(depth + 1u));
+    } else {
+      ctr->overflow = 1u;
+    }
+  }
+  uint32_t fi = warp_append(tail_out, want_refr);
+  if (want_refr) {
+    if (fi < qout.capacity) {
+      float n1, n2;
+      if (refr == 1.0f) {
+        n1 = 1.0f, n2 = ni.refr_coeff;
+      } else {
+        n1 = ni.refr_coeff, n2 = 1.0f;
+      }
+      V3 along = s.n * dot(d, s.n);
+      V3 tangent = d - along;
+      V3 nd = normalize(along + tangent * (n2 / n1));
+      V3 no = pt + nd * 0.001f;
+      qout.a[fi] = make_float4(no.x, no.y, no.z, nd.x);
+      qout.b[fi] = make_float4(nd.y, nd.z, weight * (1.0f - alpha), energy);
+      qout.c[fi] = make_float4(n2, __uint_as_float(gid), __uint_as_float(path * 2u + 1u), __uint_as_float(depth + 1u));
+    } else {
+      ctr->overflow = 1u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5 — resolve: pixel = tot_c / spp (src/scene.rs:94); optional RGB8 (src/image.rs:64-77)
+// ---------------------------------------------------------------------------------------------
+__global__ void resolve_kernel(const float4 *accum, uint32_t n, float spp, float *out_rgb) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 a = accum[i];
+  out_rgb[3 * (size_t)i + 0] = a.x / spp;
+  out_rgb[3 * (size_t)i + 1] = a.y / spp;
+  out_rgb[3 * (size_t)i + 2] = a.z / spp;
+}
+
+__global__ void resolve_rgb8_kernel(const float4 *accum, uint32_t n, float spp, uint8_t *out_rgb8) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 a = accum[i];
+  float c[3] = {a.x / spp, a.y / spp, a.z / spp};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float v = fminf(fmaxf(c[k] * 255.0f, 0.0f), 255.0f);  // inf(sup(color, 0), 255) then `as usize` truncation
+    out_rgb8[3 * (size_t)i + k] = (uint8_t)(unsigned)v;
+  }
+}
+
+// K6 — packed tiles of n_ranks ranks (rank r owns tiles r, r+n_ranks, ...) -> row-major image
+__global__ void untile_kernel(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width,
+                              uint32_t height, uint32_t tiles_x, float *out_rgb) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= width * height) return;
+  uint32_t y = i / width, x = i - y * width;
+  uint32_t tile = (y / NRB_TILE) * tiles_x + (x / NRB_TILE);
+  uint32_t rank = tile % n_ranks, lt = tile / n_ranks;
+  size_t src = ((size_t)rank * tiles_per_rank + lt) * (NRB_TILE * NRB_TILE) + (y % NRB_TILE) * NRB_TILE + (x % NRB_TILE);
+  out_rgb[3 * (size_t)i + 0] = gathered[3 * src + 0];
+  out_rgb[3 * (size_t)i + 1] = gathered[3 * src + 1];
+  out_rgb[3 * (size_t)i + 2] = gathered[3 * src + 2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------------------------
+void launch_raygen(const FrameParams &fp, uint32_t slot_begin, uint32_t slot_end, RayQueue q, uint32_t *tail,
+                   cudaStream_t st) {
+  uint32_t n = slot_end - slot_begin;
+  if (!n) return;
+  raygen_kernel<<<(n + 255) / 256, 256, 0, st>>>(fp, slot_begin, slot_end, q, tail);
+}
+
+void launch_trace_closest(const SceneView &sc, bool has_shapes, RayQueue q, float4 *hits, const uint32_t *count,
+                          uint32_t *fetch, int grid, cudaStream_t st) {
+  if (has_shapes)
+    trace_closest_kernel<true><<<grid, kTraceBlock, 0, st>>>(sc, q, hits, count, fetch);
+  else
+    trace_closest_kernel<false><<<grid, kTraceBlock, 0, st>>>(sc, q, hits, count, fetch);
+}
+
+void launch_trace_shadow(const SceneView &sc, bool has_shapes, ShadowQueue q, float4 *accum, const uint32_t *count,
+                         uint32_t *fetch, int grid, cudaStream_t st) {
+  if (has_shapes)
+    trace_shadow_kernel<true><<<grid, kTraceBlock, 0, st>>>(sc, q, accum, count, fetch);
+  else
+    trace_shadow_kernel<false><<<grid, kTraceBlock, 0, st>>>(sc, q, accum, count, fetch);
+}
+
+void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, RayQueue qin, const float4 *hits,
+                  uint32_t lo, uint32_t hi, RayQueue qout, uint32_t *tail_out, ShadowQueue sq, Counters *ctr,
+                  float4 *accum, cudaStream_t st) {
+  uint32_t n = hi - lo;
+  if (!n) return;
+  uint32_t grid = (n + kShadeBlock - 1) / kShadeBlock;
+  if (has_shapes)
+    shade_kernel<true><<<grid, kShadeBlock, 0, st>>>(sc, fp, qin, hits, lo, hi, qout, tail_out, sq, ctr, accum);
+  else
+    shade_kernel<false><<<grid, kShadeBlock, 0, st>>>(sc, fp, qin, hits, lo, hi, qout, tail_out, sq, ctr, accum);
+}
+
+void launch_resolve(const float4 *accum, uint32_t n, uint32_t spp, float *out_rgb, cudaStream_t st) {
+  if (!n) return;
+  resolve_kernel<<<(n + 255) / 256, 256, 0, st>>>(accum, n, (float)spp, out_rgb);
+}
+
+void launch_resolve_rgb8(const float4 *accum, uint32_t n, uint32_t spp, uint8_t *out, cudaStream_t st) {
+  if (!n) return;
+  resolve_rgb8_kernel<<<(n + 255) / 256, 256, 0, st>>>(accum, n, (float)spp, out);
+}
+
+void launch_untile(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width, uint32_t height,
+                   float *out_rgb, cudaStream_t st) {
+  uint32_t n = width * height;
+  uint32_t tiles_x = (width + NRB_TILE - 1) / NRB_TILE;
+  untile_kernel<<<(n + 255) / 256, 256, 0, st>>>(gathered, n_ranks, tiles_per_rank, width, height, tiles_x, out_rgb);
+}
+
+int trace_blocks_per_sm(bool has_shapes, bool shadow) {
+  int nb = 0;
+  if (shadow) {
+    if (has_shapes)
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_shadow_kernel<true>, kTraceBlock, 0);
+    else
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_shadow_kernel<false>, kTraceBlock, 0);
+  } else {
+    if (has_shapes)
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_closest_kernel<true>, kTraceBlock, 0);
+    else
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_closest_kernel<false>, kTraceBlock, 0);
+  }
+  return nb > 0 ? nb : 1;
+}
+
+}  // namespace nrb
