@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s (primary + secondary) of the nrays render hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config C3]
+
+A "step" is one frame: scene::render (src/scene.rs:29-116) of BASELINE.json's headline workload,
+crytek_sponza.scene at 1920x1080x4spp (config C3; the mesh is the seeded synthetic stand-in, the
+real asset is not in the reference tree).  At N > 1 (torchrun, one rank per GPU) the SAME frame is
+tile-sharded over the ranks and collected by one NCCL all-gather -> strong scaling.
+
+  value     whole-job Mrays/s with everything resident in HBM (nrb_render_device / tiles+gather)
+  e2e       same metric through the host-facing C-ABI call nrb_render: camera arguments in, image
+            copied back to pinned host memory inside the timed region
+  roofline  dominant kernel's algorithmic bytes / CUDA-event launch time vs the measured HBM peak
+  cpu_baseline / --impl reference
+            the CPU oracle (C++ restatement of the reference path; the Rust reference itself cannot
+            be built here) on all host cores, on a bounded sample of the same frame
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/s (primary+secondary) at 1920x1080; HBM GB/s vs peak"
+UNIT = "Mrays/s"
+SAMPLE_BANDS = 9       # cpu sample: 9 bands of 12 rows spread over the frame (10 % of the pixels)
+SAMPLE_ROWS = 12
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(cfg, threads=0, repeats=1):
+    """Time the CPU oracle on SAMPLE_BANDS x SAMPLE_ROWS rows of the frame. Returns (Mrays/s, rays, seconds, cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle_lib as O
+    from nrays_b200 import configs, make_camera
+
+    scene, camdesc, c = configs.build_flat(cfg)
+    w, h = c["width"], c["height"]
+    cam = make_camera(w, h, c["spp"], c["window"], camdesc.eye, camdesc.projection((w, h)), seed=0)
+    osc = O.OracleScene(scene.flat, 64)
+    cores = os.cpu_count() if threads <= 0 else threads
+    out = np.zeros((w * h, 3), np.float32)
+    rays, secs = 0, 0.0
+    for _ in range(repeats):
+        for b in range(SAMPLE_BANDS):
+            y0 = max(0, int((b + 0.5) * h / SAMPLE_BANDS) - SAMPLE_ROWS // 2)
+            rows = min(SAMPLE_ROWS, h - y0)
+            t0 = time.perf_counter()
+            _, st = osc.render(cam, cores, y0 * w, rows * w, out)
+            secs += time.perf_counter() - t0
+            rays += st.rays_total
+    return rays / secs / 1e6, rays, secs, cores
+
+
+def sample_label(cfg_name):
+    return "%d bands x %d rows (%.0f %% of the frame's pixels, all spp) of %s" % (
+        SAMPLE_BANDS, SAMPLE_ROWS, 100.0 * SAMPLE_BANDS * SAMPLE_ROWS / 1080.0, cfg_name)
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU path (oracle restatement; kind "port") on all host cores."""
+    if rank != 0:
+        return
+    from nrays_b200 import configs
+
+    cfg = configs.CONFIGS[args.config]
+    for _ in range(args.warmup):
+        cpu_sample(args.config)
+    t_total, rays_total = 0.0, 0
+    cores = os.cpu_count()
+    for _ in range(args.steps):
+        v, rays, secs, cores = cpu_sample(args.config)
+        t_total += secs
+        rays_total += rays
+    value = rays_total / t_total / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["name"], "resolution": [cfg["width"], cfg["height"]], "spp": cfg["spp"],
+                   "sample": sample_label(cfg["name"])},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample_label(cfg["name"]),
+                         "note": "C++ f64 restatement of the reference path (oracle/); the Rust reference cannot be "
+                                 "built in this image (no rustc/cargo, ncollide3d un-vendored)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+
+    from nrays_b200 import _abi as A
+    from nrays_b200 import _lib, configs, dist, make_camera
+
+    lib = _lib.load()  # raises if the CUDA library is missing: no CPU fallback
+    if lib.nrb_device_count() <= local_rank:
+        raise RuntimeError("bench.py needs a CUDA device per rank (found %d)" % lib.nrb_device_count())
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as td
+
+        td.init_process_group("nccl", device_id=dev)
+    cfg = configs.CONFIGS[args.config]
+    scene, camdesc, _ = configs.build(args.config, device=local_rank)
+    w, h, spp, window = cfg["width"], cfg["height"], cfg["spp"], cfg["window"]
+    proj = camdesc.projection((w, h))
+    stream = torch.cuda.current_stream()
+    dist.use_stream(scene, stream.cuda_stream)
+
+    out = torch.empty(h * w * 3, dtype=torch.float32, device=dev)
+    tpr = dist.tiles_per_rank(w, h, world)
+    packed = torch.zeros((tpr, 16, 16, 3), dtype=torch.float32, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    host_ptr = lib.nrb_host_alloc(h * w * 3 * 4)  # pinned destination of the e2e image
+    host_img = np.ctypeslib.as_array(C.cast(host_ptr, C.POINTER(C.c_float)), shape=(h * w * 3,))
+    pinned_t = torch.empty(h * w * 3, dtype=torch.float32).pin_memory() if world > 1 else None
+
+    def cam_for(step):
+        return make_camera(w, h, spp, window, camdesc.eye, proj, seed=step)
+
+    def step_device(step):
+        cam = cam_for(step)
+        if world == 1:
+            return dist.render_device(scene, cam, out), 0
+        st, _n = dist.render_tiles_device(scene, cam, rank, world, packed)
+        g = dist.all_gather_tiles(packed, world)
+        if rank == 0:
+            dist.untile_device(g, world, w, h, out, device=local_rank, stream=stream.cuda_stream)
+            return st, 1
+        return st, 0
+
+    def step_e2e(step):
+        cam = cam_for(step)
+        if world == 1:
+            st = A.NrbStats()
+            _lib.check(lib.nrb_render(scene.handle, C.byref(cam), C.cast(host_ptr, C.POINTER(C.c_float)), C.byref(st)))
+            return st, 0
+        st, extra = step_device(step)
+        if rank == 0:
+            pinned_t.copy_(out, non_blocking=True)
+            stream.synchronize()
+        return st, extra
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, first_step):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        stats = []
+        barrier()
+        for i in range(steps):
+            flush.zero_()  # evict L2 between timed frames (outside the event pair)
+            evs[i][0].record(stream)
+            st, extra = fn(first_step + i)
+            evs[i][1].record(stream)
+            stats.append((st.as_dict(), extra))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        return ms, stats
+
+    for i in range(args.warmup):
+        step_device(1000 + i)
+    for i in range(max(1, min(args.warmup, 2))):
+        step_e2e(2000 + i)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    ms_dev, stats_dev = timed(step_device, args.steps, 0)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, stats_e2e = timed(step_e2e, args.steps, 0)
+
+    def reduce(ms, stats):
+        rays = sum(s["rays_total"] for s, _ in stats)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        r = torch.tensor([float(rays)], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            td.all_reduce(r, op=td.ReduceOp.SUM)
+        return float(t.item()), float(r.item())
+
+    ms_dev_max, rays_dev = reduce(ms_dev, stats_dev)
+    ms_e2e_max, rays_e2e = reduce(ms_e2e, stats_e2e)
+    launches = sum(s["kernel_launches"] + extra for s, extra in stats_dev)
+    lt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(lt, op=td.ReduceOp.SUM)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        s0 = stats_dev[0][0]
+        geom_bytes = s0["bvh_nodes"] * 64 + s0["triangles"] * 48
+        n_closest = sum(s["rays_primary"] + s["rays_reflect"] + s["rays_refract"] for s, _ in stats_dev)
+        n_shadow = sum(s["rays_shadow"] for s, _ in stats_dev)
+        ms_closest = sum(s["ms_closest"] for s, _ in stats_dev)
+        ms_shadow = sum(s["ms_shadow"] for s, _ in stats_dev)
+        l_closest = sum(s["launches_closest"] for s, _ in stats_dev)
+        l_shadow = sum(s["launches_shadow"] for s, _ in stats_dev)
+        if ms_closest >= ms_shadow:
+            kname, rays_k, ms_k, l_k, per_ray = "trace_closest_kernel", n_closest, ms_closest, l_closest, 48
+        else:
+            kname, rays_k, ms_k, l_k, per_ray = "trace_shadow_kernel", n_shadow, ms_shadow, l_shadow, 64
+        bytes_k = rays_k * per_ray + l_k * geom_bytes
+        achieved = bytes_k / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
+        n_primary = sum(s["rays_primary"] for s, _ in stats_dev)
+        frame_bytes = 160 * (n_closest + n_shadow) + 16 * n_primary + len(stats_dev) * s0["scene_bytes"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(kname)
+            except Exception:
+                traffic = None
+        roofline = {
+            "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "bytes_per_launch": bytes_k / max(1, l_k), "ms_per_launch": ms_k / max(1, l_k),
+            "kernel_share_of_step": ms_k / ms_dev if ms_dev > 0 else None,
+            "frame": {"algorithmic_bytes_per_step": frame_bytes / len(stats_dev),
+                      "achieved": frame_bytes / (ms_dev_max * 1e-3) / 1e9, "frac": frame_bytes / (ms_dev_max * 1e-3) / 1e9 / peak},
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, rays, secs, cores = cpu_sample(args.config, repeats=4)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": sample_label(cfg["name"]) + " x4 repeats (%.1f s of CPU work)" % secs}
+        line = {
+            "metric": METRIC, "value": rays_dev / (ms_dev_max * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "resolution": [w, h], "spp": spp, "window": window,
+                       "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
+                       "sharding": "none" if world == 1 else "16x16 tiles round-robin over %d ranks + one NCCL all-gather" % world,
+                       "rays_per_step": rays_dev / args.steps},
+            "e2e": {"value": rays_e2e / (ms_e2e_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(A.NrbCamera),
+                    "d2h_bytes_per_step": w * h * 3 * 4, "ms_per_step": ms_e2e_max / args.steps},
+            "gpu_launches": int(lt.item()),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    lib.nrb_host_free(host_ptr)
+    scene.close()
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1 and args.impl == "ours":
+        # convenience: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--config", args.config]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -173,6 +173,10 @@ typedef struct NrbStats {
   uint64_t bvh_nodes;       /* device BVH size, for the roofline's scene_bytes */
   uint64_t triangles;
   uint64_t scene_bytes;
+  float ms_closest;         /* CUDA-event time of the closest-hit traversal launches */
+  float ms_shadow;          /* CUDA-event time of the shadow traversal launches */
+  uint32_t launches_closest;
+  uint32_t launches_shadow;
 } NrbStats;
 
 typedef struct NrbScene NrbScene; /* opaque handle == Arc<Scene> of the reference */
@@ -192,6 +196,11 @@ void nrb_scene_destroy(NrbScene *scene);
 
 /* Replaces Scene::set_background (src/scene.rs:136-139). */
 int nrb_scene_set_background(NrbScene *scene, const float rgb[3]);
+
+/* Runs all of this scene's device work on `cuda_stream` (a cudaStream_t owned by the caller, e.g. the
+ * harness's current stream, so one pair of events brackets render + collective); NULL restores the
+ * scene's own non-blocking stream.  The reference's render is synchronous; so is ours on any stream. */
+int nrb_scene_set_stream(NrbScene *scene, void *cuda_stream);
 
 /* Replaces scene::render (src/scene.rs:29-116).  `out_rgb` is a HOST buffer of
  * width*height*3 floats, row-major, pixel (x,y) at 3*(x + y*width) — the layout of
@@ -214,9 +223,10 @@ uint32_t nrb_tile_count_local(uint32_t width, uint32_t height, const NrbTileSet 
 
 /* After the gather: scatter `n_ranks` packed tile buffers laid end to end in DEVICE memory
  * (rank r owning tiles r, r+n_ranks, ...; each rank's buffer padded to `tiles_per_rank` tiles)
- * into a row-major width*height*3 DEVICE image. */
-int nrb_untile_device(int device, const float *d_gathered, uint32_t n_ranks, uint32_t tiles_per_rank,
-                      uint32_t width, uint32_t height, float *d_out_rgb);
+ * into a row-major width*height*3 DEVICE image.  Runs on `cuda_stream` (NULL = default stream) and
+ * returns after it completed. */
+int nrb_untile_device(int device, void *cuda_stream, const float *d_gathered, uint32_t n_ranks,
+                      uint32_t tiles_per_rank, uint32_t width, uint32_t height, float *d_out_rgb);
 
 /* "Next" row 8f-2: Image::to_png's quantisation (src/image.rs:64-77): clamp(c*255, 0, 255) truncated
  * to u8, RGB8 row-major, on device; `out_rgb8` is a HOST buffer of width*height*3 bytes. */

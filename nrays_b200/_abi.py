@@ -141,6 +141,10 @@ class NrbStats(C.Structure):
         ("bvh_nodes", C.c_uint64),
         ("triangles", C.c_uint64),
         ("scene_bytes", C.c_uint64),
+        ("ms_closest", C.c_float),
+        ("ms_shadow", C.c_float),
+        ("launches_closest", C.c_uint32),
+        ("launches_shadow", C.c_uint32),
     ]
 
     @property
@@ -159,6 +163,7 @@ EXPORTS = [
     "nrb_scene_create",
     "nrb_scene_destroy",
     "nrb_scene_set_background",
+    "nrb_scene_set_stream",
     "nrb_render",
     "nrb_render_device",
     "nrb_render_tiles_device",

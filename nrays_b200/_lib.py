@@ -35,6 +35,8 @@ def load():
     lib.nrb_scene_destroy.restype = None
     lib.nrb_scene_set_background.argtypes = [vp, C.POINTER(C.c_float)]
     lib.nrb_scene_set_background.restype = C.c_int
+    lib.nrb_scene_set_stream.argtypes = [vp, vp]
+    lib.nrb_scene_set_stream.restype = C.c_int
     lib.nrb_render.argtypes = [vp, C.POINTER(A.NrbCamera), f32p, C.POINTER(A.NrbStats)]
     lib.nrb_render.restype = C.c_int
     lib.nrb_render_device.argtypes = [vp, C.POINTER(A.NrbCamera), vp, C.POINTER(A.NrbStats)]
@@ -46,7 +48,7 @@ def load():
     lib.nrb_tile_count.restype = u32
     lib.nrb_tile_count_local.argtypes = [u32, u32, C.POINTER(A.NrbTileSet)]
     lib.nrb_tile_count_local.restype = u32
-    lib.nrb_untile_device.argtypes = [C.c_int, vp, u32, u32, u32, u32, vp]
+    lib.nrb_untile_device.argtypes = [C.c_int, vp, vp, u32, u32, u32, u32, vp]
     lib.nrb_untile_device.restype = C.c_int
     lib.nrb_render_rgb8.argtypes = [vp, C.POINTER(A.NrbCamera), C.POINTER(C.c_uint8), C.POINTER(A.NrbStats)]
     lib.nrb_render_rgb8.restype = C.c_int

@@ -73,7 +73,8 @@ size_t env_size(const char *name, size_t dflt) {
 
 struct NrbScene {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // stream in use
+  cudaStream_t own_stream = nullptr;  // created by the library
   int sm_count = 148;
   // scene tables
   DevBuf d_nodes, d_tris, d_tri_uvs, d_shapes, d_node_info, d_materials, d_textures, d_texels, d_lights, d_planes,
@@ -96,7 +97,7 @@ struct NrbScene {
     for (auto e : events) cudaEventDestroy(e);
     if (ev_begin) cudaEventDestroy(ev_begin);
     if (ev_end) cudaEventDestroy(ev_end);
-    if (stream) cudaStreamDestroy(stream);
+    if (own_stream) cudaStreamDestroy(own_stream);
   }
 };
 
@@ -144,7 +145,9 @@ int relayout_bfs(std::vector<BvhNode> &nodes, int &root_all, int &root_opaque, s
 int build_scene(const NrbSceneDesc &d, NrbScene &S) {
   if (d.n_nodes && !d.nodes) return fail(NRB_ERR_INVALID_ARG, "nodes is NULL");
   if (d.n_lights && !d.lights) return fail(NRB_ERR_INVALID_ARG, "lights is NULL");
-  if (d.n_materials == 0 || !d.materials) return fail(NRB_ERR_INVALID_ARG, "scene has no materials");
+  if (d.n_materials && !d.materials) return fail(NRB_ERR_INVALID_ARG, "materials is NULL");
+  if (d.n_textures && !d.textures) return fail(NRB_ERR_INVALID_ARG, "textures is NULL");
+  if (d.n_texels && !d.texels) return fail(NRB_ERR_INVALID_ARG, "texels is NULL");
   if (d.n_texels >= 0xFFFFFFFFull) return fail(NRB_ERR_INVALID_ARG, "texel pool too large (>= 2^32 texels)");
 
   std::vector<Texture> textures(d.n_textures);
@@ -544,7 +547,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   Counters *dc = S.d_counters.as<Counters>();
   uint32_t launches = 0, waves = 0;
   size_t ev_used = 0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_spans;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> closest_spans, shadow_spans;
 
   CU(cudaEventRecord(S.ev_begin, st));
   CU(cudaMemsetAsync(accum, 0, (size_t)n_acc * 16, st));
@@ -603,7 +606,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
       launch_trace_closest(S.view, S.has_shapes, ray_queue(S, cur), S.d_hits.as<float4>(), &dc->n_rays[cur],
                            &dc->fetch_closest, S.grid_closest, st);
       CU(cudaEventRecord(e1, st));
-      trace_spans.emplace_back(e0, e1);
+      closest_spans.emplace_back(e0, e1);
       ++launches;
       // K4 shade (+ K3 shadow) in chunks bounded by the shadow queue
       for (uint32_t lo = 0; lo < n; lo += chunk) {
@@ -618,7 +621,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
           CU(cudaEventRecord(s0, st));
           launch_trace_shadow(S.view, S.has_shapes, sq, accum, &dc->n_shadow, &dc->fetch_shadow, S.grid_shadow, st);
           CU(cudaEventRecord(s1, st));
-          trace_spans.emplace_back(s0, s1);
+          shadow_spans.emplace_back(s0, s1);
           ++launches;
         }
       }
@@ -647,14 +650,23 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, S.ev_begin, S.ev_end);
     stats->ms_device = ms;
-    float tr = 0.0f;
-    for (auto &sp : trace_spans) {
+    float tc = 0.0f, ts = 0.0f;
+    for (auto &sp : closest_spans) {
       float t = 0.0f;
       cudaEventElapsedTime(&t, sp.first, sp.second);
-      tr += t;
+      tc += t;
     }
-    stats->ms_trace = tr;
-    stats->ms_shade = ms - tr;
+    for (auto &sp : shadow_spans) {
+      float t = 0.0f;
+      cudaEventElapsedTime(&t, sp.first, sp.second);
+      ts += t;
+    }
+    stats->ms_closest = tc;
+    stats->ms_shadow = ts;
+    stats->launches_closest = (uint32_t)closest_spans.size();
+    stats->launches_shadow = (uint32_t)shadow_spans.size();
+    stats->ms_trace = tc + ts;
+    stats->ms_shade = ms - (tc + ts);
     stats->bvh_nodes = S.n_bvh_nodes;
     stats->triangles = S.n_tris;
     stats->scene_bytes = S.scene_bytes;
@@ -696,7 +708,8 @@ int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out) {
   std::unique_ptr<NrbScene> S(new NrbScene);
   S->device = device;
   S->sm_count = prop.multiProcessorCount;
-  CU(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&S->own_stream, cudaStreamNonBlocking));
+  S->stream = S->own_stream;
   CU(cudaEventCreate(&S->ev_begin));
   CU(cudaEventCreate(&S->ev_end));
   CU(cudaHostAlloc((void **)&S->h_counters, sizeof(Counters), cudaHostAllocDefault));
@@ -714,6 +727,14 @@ void nrb_scene_destroy(NrbScene *scene) { delete scene; }
 int nrb_scene_set_background(NrbScene *scene, const float rgb[3]) {
   if (!scene || !rgb) return fail(NRB_ERR_INVALID_ARG, "scene/rgb is NULL");
   for (int k = 0; k < 3; ++k) scene->view.background[k] = rgb[k];
+  return NRB_OK;
+}
+
+int nrb_scene_set_stream(NrbScene *scene, void *cuda_stream) {
+  if (!scene) return fail(NRB_ERR_INVALID_ARG, "scene is NULL");
+  CU(cudaSetDevice(scene->device));
+  CU(cudaStreamSynchronize(scene->stream));
+  scene->stream = cuda_stream ? (cudaStream_t)cuda_stream : scene->own_stream;
   return NRB_OK;
 }
 
@@ -762,12 +783,13 @@ uint32_t nrb_tile_count_local(uint32_t width, uint32_t height, const NrbTileSet 
   return (n - tiles->first + tiles->stride - 1) / tiles->stride;
 }
 
-int nrb_untile_device(int device, const float *d_gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width,
-                      uint32_t height, float *d_out_rgb) {
+int nrb_untile_device(int device, void *cuda_stream, const float *d_gathered, uint32_t n_ranks,
+                      uint32_t tiles_per_rank, uint32_t width, uint32_t height, float *d_out_rgb) {
   if (!d_gathered || !d_out_rgb || n_ranks == 0) return fail(NRB_ERR_INVALID_ARG, "untile: bad arguments");
   CU(cudaSetDevice(device));
-  launch_untile(d_gathered, n_ranks, tiles_per_rank, width, height, d_out_rgb, 0);
-  CU(cudaStreamSynchronize(0));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  launch_untile(d_gathered, n_ranks, tiles_per_rank, width, height, d_out_rgb, st);
+  CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
   return NRB_OK;
 }

@@ -1,0 +1,215 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the same
+flattened scene, seeded inputs, sizes the oracle finishes in seconds.  Tolerance: per-channel
+|delta| <= 1/255 on >= 99.9 % of pixels (util.TOL / MAX_FRAC_OVER; f32 device vs f64 reference)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from nrays_b200 import (Ball, Capsule, Cone, Cuboid, Cylinder, ImageData, Interpolation, Isometry3, Light,
+                        NormalMaterial, Overflow, PhongMaterial, Plane, Scene, SceneNode, Texture2d, TriMesh, UVMaterial,
+                        _abi as A, _lib, camera_projection, configs, make_camera, render)
+from util import (TOL, assert_counts_close, assert_parity, checker_texture, default_phong, image_metrics, node, quad_mesh,
+                  render_both)
+
+pytestmark = pytest.mark.gpu
+
+
+def phong(ka=(0.1, 0.1, 0.1), kd=(0.8, 0.7, 0.6), ks=(0.5, 0.5, 0.5), ns=40.0, tex=None, amap=None):
+    return PhongMaterial(ka, kd, ks, tex, amap, ns)
+
+
+def zoo(materials):
+    shapes = [Ball(0.8), Cuboid((0.6, 0.5, 0.7)), Cylinder(0.7, 0.5), Capsule(0.5, 0.35), Cone(0.8, 0.6)]
+    nodes = []
+    for i, (g, m) in enumerate(zip(shapes, materials)):
+        nodes.append(node(g, m, pos=(-3.2 + 1.6 * i, 0.2 * (i % 2), 0.3 * i), angle=(20 * i, 35 * i, 10 * i)))
+    nodes.append(node(Plane((0, 1, 0)), phong(), pos=(0, -1.2, 0)))
+    return nodes
+
+
+def test_shape_zoo_phong(gpu):
+    tex = Texture2d(checker_texture(16, 8), Interpolation.Bilinear, Overflow.Wrap)
+    mats = [phong(tex=tex), phong(tex=tex), phong(), phong(kd=(0.2, 0.9, 0.3)), phong(ks=(0, 0, 0))]
+    lights = [Light((2, 4, -3), 0.0, 1, (1.0, 0.9, 0.8)), Light((-3, 2, -2), 0.0, 1, (0.3, 0.3, 0.5))]
+    img, st, ref, ost = render_both(zoo(mats), lights, eye=(0.5, 2.0, -7.0), w=160, h=96)
+    assert_parity(img, ref, what="zoo/phong")
+    assert_counts_close(st, ost)
+
+
+def test_shape_zoo_debug_materials_and_texture_modes(gpu):
+    t1 = Texture2d(checker_texture(5, 9, 4), Interpolation.Nearest, Overflow.ClampToEdges)
+    t2 = Texture2d(checker_texture(8, 8, 5), Interpolation.Bilinear, Overflow.ClampToEdges)
+    mats = [UVMaterial(), NormalMaterial(), UVMaterial(), NormalMaterial(), phong(tex=t1)]
+    nodes = zoo(mats) + [node(Cuboid((0.4, 0.4, 0.4)), phong(tex=t2), pos=(0, 1.5, 1.0), angle=(45, 0, 30))]
+    img, st, ref, ost = render_both(nodes, [Light((0, 5, -4), 0.0, 1, (1, 1, 1))], eye=(0.0, 1.5, -7.5), w=160, h=96)
+    assert_parity(img, ref, what="zoo/debug")
+    assert_counts_close(st, ost)
+
+
+def test_transparency_refraction_reflection_chain(gpu):
+    """alpha < 1 on every shape kind + reflective floor: refraction enters/exits, transparent shadows."""
+    glass = [phong(ka=(0.2, 0.1, 0.1)), phong(ka=(0.1, 0.2, 0.1)), phong(ka=(0.1, 0.1, 0.2)), phong(), phong()]
+    nodes = []
+    shapes = [Ball(0.8), Cuboid((0.6, 0.5, 0.7)), Cylinder(0.7, 0.5), Capsule(0.5, 0.35), Cone(0.8, 0.6)]
+    for i, (g, m) in enumerate(zip(shapes, glass)):
+        nodes.append(node(g, m, pos=(-3.2 + 1.6 * i, 0.0, 0.0), angle=(0, 15 * i, 0), alpha=0.3 + 0.1 * i, refr=1.3))
+    nodes.append(node(Plane((0, 1, 0)), phong(), pos=(0, -1.2, 0), refl=(0.3, 0.4)))
+    img, st, ref, ost = render_both(nodes, [Light((0, 5, -2), 0.0, 1, (1, 1, 1))], eye=(0.0, 2.0, -7.0), w=160, h=96)
+    assert_parity(img, ref, what="glass")
+    assert_counts_close(st, ost)
+    assert st.rays_refract > 0 and st.rays_reflect > 0
+
+
+def test_area_light_and_jitter_share_the_rng(gpu):
+    """Philox-keyed jitter + cube light samples (src/light.rs:56-63): same seed -> same image on both sides."""
+    nodes = [node(Ball(1.0), phong(), pos=(0, 0, 0)), node(Plane((0, 1, 0)), phong(), pos=(0, -1, 0))]
+    lights = [Light((1.5, 3, -1), 0.6, 10, (1, 1, 1))]  # 9 samples
+    img, st, ref, ost = render_both(nodes, lights, eye=(0, 1.5, -5), w=96, h=64, spp=3, window=1.0, seed=11)
+    assert_parity(img, ref, max_frac=2e-3, what="area light")
+    assert st.rays_shadow == ost.rays_shadow or abs(int(st.rays_shadow) - int(ost.rays_shadow)) < 0.002 * ost.rays_shadow
+    img2, _, _, _ = render_both(nodes, lights, eye=(0, 1.5, -5), w=96, h=64, spp=3, window=1.0, seed=12)
+    assert np.abs(img2 - img).max() > 1e-3  # a different seed gives a different frame
+
+
+def test_alpha_mapped_mesh_and_per_node_shadow_semantics(gpu):
+    """Opacity-mapped quads over a floor: shadows are filtered per SceneNode closest hit (F10, A.6)."""
+    rng = np.random.default_rng(0)
+    px = np.ones((16 * 16, 4), np.float32)
+    px[:, 3] = (rng.uniform(size=256) > 0.5).astype(np.float32)
+    amap = Texture2d(ImageData(px, (16, 16)), Interpolation.Nearest, Overflow.Wrap)
+    P, F, UV = quad_mesh(1.5, 6, y=1.0)
+    P2 = P.copy()
+    P2[:, 1] = 0.5
+    two_layers = TriMesh(np.concatenate([P, P2]), np.concatenate([F, F + len(P)]), np.concatenate([UV, UV * 2]))
+    Pf, Ff, UVf = quad_mesh(4.0, 8, y=-0.5)
+    nodes = [node(two_layers, phong(ka=(0.3, 0.3, 0.3), amap=amap)), node(TriMesh(Pf, Ff, UVf), phong()),
+             node(TriMesh(P + np.float32([0, 1.2, 0]), F, UV), phong(ka=(0.5, 0.2, 0.2)), alpha=0.4)]
+    img, st, ref, ost = render_both(nodes, [Light((0.5, 6, -0.5), 0.0, 1, (1, 1, 1))], eye=(0.0, 3.0, -6.0), w=160, h=120)
+    assert_parity(img, ref, max_frac=2e-3, what="alpha map")
+    assert_counts_close(st, ost)
+
+
+def test_solid_flag_and_camera_inside_objects(gpu):
+    nodes = [node(Ball(3.0), phong(), pos=(0, 0, 0), solid=False), node(Cuboid((0.5, 0.5, 0.5)), NormalMaterial(), pos=(0, 0, 1.5)),
+             node(Cylinder(0.4, 0.3), UVMaterial(), pos=(1.2, 0, 1.0))]
+    img, st, ref, ost = render_both(nodes, [Light((0, 1, 0), 0.0, 1, (1, 1, 1))], eye=(0, 0, -1.0), at=(0, 0, 1), w=96, h=64)
+    assert_parity(img, ref, what="inside ball")
+    nodes[0] = node(Ball(3.0), phong(), pos=(0, 0, 0), solid=True)   # toi 0 everywhere
+    img, st, ref, ost = render_both(nodes, [Light((0, 1, 0), 0.0, 1, (1, 1, 1))], eye=(0, 0, -1.0), at=(0, 0, 1), w=96, h=64)
+    assert_parity(img, ref, max_frac=5e-3, what="solid ball")
+
+
+def test_transparent_plane_candidate_and_plane_only_scene(gpu):
+    nodes = [node(Plane((0, 0, -1)), phong(ka=(0.2, 0.3, 0.4)), pos=(0, 0, 2), alpha=0.5),
+             node(Plane((0, 1, 0)), phong(), pos=(0, -1, 0)), node(Ball(0.7), phong(), pos=(0.3, 0, 4))]
+    img, st, ref, ost = render_both(nodes, [Light((0, 3, -3), 0.0, 1, (1, 1, 1))], eye=(0, 1, -4), w=96, h=64)
+    assert_parity(img, ref, what="transparent plane")
+    assert_counts_close(st, ost)
+    img, st, ref, ost = render_both(nodes[:2], [Light((0, 3, -3), 0.0, 1, (1, 1, 1))], eye=(0, 1, -4), w=64, h=48)
+    assert_parity(img, ref, what="planes only")
+
+
+def test_depth_cap_matches_oracle(gpu):
+    mir = [node(Plane((0, 1, 0)), NormalMaterial(), pos=(0, -1, 0), refl=(0.6, 0.0)),
+           node(Plane((0, -1, 0)), NormalMaterial(), pos=(0, 1, 0), refl=(0.6, 0.0)),
+           node(Plane((0, 0, -1)), UVMaterial(), pos=(0, 0, 6))]
+    img, st, ref, ost = render_both(mir, [], eye=(0, 0.2, -3), at=(0, 0.1, 0), w=64, h=48, max_depth=9)
+    assert_parity(img, ref, what="mirror box")
+    assert st.paths_truncated == ost.paths_truncated > 0
+    assert st.rays_reflect == ost.rays_reflect
+
+
+def test_empty_scene_and_background(gpu):
+    img, st, ref, ost = render_both([], [], eye=(0, 0, -3), w=33, h=17, background=(0.25, 0.5, 0.75))
+    np.testing.assert_allclose(img, np.tile(np.float32([0.25, 0.5, 0.75]), (33 * 17, 1)))
+    np.testing.assert_allclose(ref, img)
+    assert st.rays_primary == 33 * 17 and st.rays_total == 33 * 17
+    scene = Scene([node(Ball(1.0), NormalMaterial(), pos=(0, 0, 50))], [], (1, 1, 1))
+    scene.set_background((0.1, 0.2, 0.3))
+    out = render(scene, (8, 8), 1, 0.0, (0, 0, 0), camera_projection((0, 0, 0), (0, 1, 0.01), 30, 8, 8))
+    np.testing.assert_allclose(out.pixels, np.tile(np.float32([0.1, 0.2, 0.3]), (64, 1)))
+    scene.close()
+
+
+@pytest.mark.parametrize("w,h,spp", [(1, 1, 1), (17, 9, 2), (16, 16, 1), (31, 33, 5)])
+def test_ragged_resolutions(gpu, w, h, spp):
+    nodes = [node(Ball(1.0), phong(), pos=(0, 0, 0)), node(Plane((0, 1, 0)), NormalMaterial(), pos=(0, -1, 0))]
+    img, st, ref, ost = render_both(nodes, [Light((2, 3, -2), 0.0, 1, (1, 1, 1))], eye=(0, 1, -4), w=w, h=h, spp=spp, window=1.0, seed=4)
+    assert st.rays_primary == w * h * spp
+    m = image_metrics(img, ref)
+    assert m["frac_over"] <= max(2.0 / (w * h), 2e-3), m
+
+
+def test_error_codes(gpu):
+    lib = gpu
+    scene = Scene([node(Ball(1.0), NormalMaterial())], [], (1, 1, 1))
+    out = np.zeros((16, 3), np.float32)
+    outp = out.ctypes.data_as(C.POINTER(C.c_float))
+    P = camera_projection((0, 0, -3), (0, 0, 0), 45, 4, 4)
+    cam = make_camera(4, 4, 0, 0.0, (0, 0, -3), P)               # assert!(ray_per_pixel > 0): src/scene.rs:37
+    assert lib.nrb_render(scene.handle, C.byref(cam), outp, None) == A.NRB_ERR_INVALID_ARG
+    assert b"ray_per_pixel" in lib.nrb_last_error()
+    cam = make_camera(0, 4, 1, 0.0, (0, 0, -3), P)
+    assert lib.nrb_render(scene.handle, C.byref(cam), outp, None) == A.NRB_ERR_INVALID_ARG
+    cam = make_camera(4, 4, 1, 0.0, (0, 0, -3), np.zeros((4, 4)))  # w == 0: from_homogeneous().unwrap() panics
+    assert lib.nrb_render(scene.handle, C.byref(cam), outp, None) == A.NRB_ERR_INVALID_ARG
+    assert lib.nrb_render(scene.handle, None, outp, None) == A.NRB_ERR_INVALID_ARG
+    scene.close()
+    # malformed tables
+    flat = Scene([node(Ball(1.0), NormalMaterial())], [], upload=False).flat
+    flat.node_rows[0].material = 7
+    h = C.c_void_p()
+    assert lib.nrb_scene_create(C.byref(flat.desc), 0, C.byref(h)) == A.NRB_ERR_INVALID_ARG
+    flat = Scene([node(Ball(1.0), NormalMaterial())], [], upload=False).flat
+    flat.node_rows[0].nmap_texture = 0
+    assert lib.nrb_scene_create(C.byref(flat.desc), 0, C.byref(h)) == A.NRB_ERR_UNSUPPORTED
+    Pm, Fm, UVm = quad_mesh(1.0, 1)
+    flat = Scene([node(TriMesh(Pm, Fm, UVm), NormalMaterial())], [], upload=False).flat
+    flat.indices[0] = 1000
+    assert lib.nrb_scene_create(C.byref(flat.desc), 0, C.byref(h)) == A.NRB_ERR_INVALID_ARG
+    flat = Scene([node(Ball(1.0), NormalMaterial())], [], upload=False).flat
+    assert lib.nrb_scene_create(C.byref(flat.desc), 99, C.byref(h)) == A.NRB_ERR_INVALID_ARG
+    flat.desc.abi_version = 99
+    assert lib.nrb_scene_create(C.byref(flat.desc), 0, C.byref(h)) == A.NRB_ERR_INVALID_ARG
+
+
+def test_rgb8_output_is_the_png_quantisation(gpu):
+    scene, camd, cfg = configs.build("C1", globe_size=(32, 16))
+    w = h = 64
+    cam = make_camera(w, h, 1, 0.0, camd.eye, camd.projection((w, h)))
+    f = np.empty((w * h, 3), np.float32)
+    b = np.empty((w * h, 3), np.uint8)
+    _lib.check(gpu.nrb_render(scene.handle, C.byref(cam), f.ctypes.data_as(C.POINTER(C.c_float)), None))
+    _lib.check(gpu.nrb_render_rgb8(scene.handle, C.byref(cam), b.ctypes.data_as(C.POINTER(C.c_uint8)), None))
+    exp = np.clip(f * np.float32(255.0), 0, 255).astype(np.uint8)       # src/image.rs:64-77
+    assert (np.abs(exp.astype(int) - b.astype(int)) > 1).mean() == 0     # atomics order can flip a +-1 boundary
+    assert (exp != b).mean() < 0.01
+    scene.close()
+
+
+def test_tile_sharded_render_equals_full_frame(gpu):
+    """8 virtual ranks on one GPU: packed tiles + un-tile == the unsharded frame (RNG keyed by global pixel)."""
+    import torch
+
+    from nrays_b200 import dist
+
+    scene, camd, cfg = configs.build("C3", target_tris=30000, lod=4)
+    w, h, world = 200, 120, 8
+    cam = make_camera(w, h, 2, 1.0, camd.eye, camd.projection((w, h)), seed=5)
+    full = torch.empty(h * w * 3, dtype=torch.float32, device="cuda")
+    st_full = dist.render_device(scene, cam, full)
+    tpr = dist.tiles_per_rank(w, h, world)
+    packed = torch.zeros((world, tpr, 16, 16, 3), dtype=torch.float32, device="cuda")
+    rays = 0
+    for r in range(world):
+        st, n_local = dist.render_tiles_device(scene, cam, r, world, packed[r])
+        assert n_local == len(dist.local_tiles(w, h, r, world))
+        rays += st.rays_total
+    out = torch.empty(h * w * 3, dtype=torch.float32, device="cuda")
+    dist.untile_device(packed, world, w, h, out)
+    assert rays == st_full.rays_total
+    np.testing.assert_allclose(out.cpu().numpy(), full.cpu().numpy(), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(dist.untile_host(packed.cpu().numpy(), world, w, h).reshape(-1), full.cpu().numpy(), atol=2e-6)
+    scene.close()
