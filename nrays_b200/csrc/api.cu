@@ -88,12 +88,16 @@ struct NrbScene {
   DevBuf d_q[2][3], d_hits, d_sq[3], d_accum, d_counters, d_out, d_out8;
   uint32_t q_cap[2] = {0, 0}, sq_cap = 0, hits_cap = 0;
   Counters *h_counters = nullptr;  // pinned mirror
+  uint32_t *h_wave_counts = nullptr;  // pinned: exact ray count of every wave of the current frame
+  size_t h_wave_cap = 0;
+  int grid_shade = 148;
   std::vector<cudaEvent_t> events;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 
   ~NrbScene() {
     cudaSetDevice(device);
     if (h_counters) cudaFreeHost(h_counters);
+    if (h_wave_counts) cudaFreeHost(h_wave_counts);
     for (auto e : events) cudaEventDestroy(e);
     if (ev_begin) cudaEventDestroy(ev_begin);
     if (ev_end) cudaEventDestroy(ev_end);
@@ -546,9 +550,23 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   float4 *accum = S.d_accum.as<float4>();
   Counters *dc = S.d_counters.as<Counters>();
   uint32_t launches = 0, waves = 0;
+  size_t wave_counts_used = 0;
   size_t ev_used = 0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> closest_spans, shadow_spans;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> closest_spans, shadow_spans, shade_spans;
+  const bool dump = getenv("NRB_DUMP_WAVES") != nullptr;
 
+  {
+    uint64_t n_batches = (fp.n_local_tiles + std::max<uint64_t>(1, env_size("NRB_BATCH_SLOTS", 8u << 20) / (NRB_TILE * NRB_TILE * fp.spp)) - 1) /
+                         std::max<uint64_t>(1, env_size("NRB_BATCH_SLOTS", 8u << 20) / (NRB_TILE * NRB_TILE * fp.spp));
+    size_t need = (size_t)(n_batches + 1) * ((size_t)fp.max_depth + 2);
+    if (need > S.h_wave_cap) {
+      CU(cudaStreamSynchronize(st));
+      if (S.h_wave_counts) cudaFreeHost(S.h_wave_counts);
+      S.h_wave_counts = nullptr;
+      CU(cudaHostAlloc((void **)&S.h_wave_counts, need * sizeof(uint32_t), cudaHostAllocDefault));
+      S.h_wave_cap = need;
+    }
+  }
   CU(cudaEventRecord(S.ev_begin, st));
   CU(cudaMemsetAsync(accum, 0, (size_t)n_acc * 16, st));
   CU(cudaMemsetAsync(dc, 0, sizeof(Counters), st));
@@ -565,38 +583,81 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   for (uint64_t tile_lo = 0; tile_lo < fp.n_local_tiles; tile_lo += tiles_per_batch) {
     uint64_t tile_hi = std::min<uint64_t>(fp.n_local_tiles, tile_lo + tiles_per_batch);
     uint32_t slot_lo = (uint32_t)(tile_lo * per_tile), slot_hi = (uint32_t)(tile_hi * per_tile);
-    (void)total_slots;
-    int cur = 0;
+    // exact number of primary rays of this batch (samples of pixels inside the image): no sync needed
+    uint64_t n0 = 0;
+    for (uint64_t lt = tile_lo; lt < tile_hi; ++lt) {
+      uint32_t tile = fp.tile_first + (uint32_t)lt * fp.tile_stride;
+      uint32_t ty = tile / fp.tiles_x, tx = tile - ty * fp.tiles_x;
+      uint32_t wpx = std::min<uint32_t>(NRB_TILE, fp.width - tx * NRB_TILE), hpx = std::min<uint32_t>(NRB_TILE, fp.height - ty * NRB_TILE);
+      n0 += (uint64_t)wpx * hpx * fp.spp;
+    }
+    primary += n0;
     CU(ensure_ray_queue(S, 0, slot_hi - slot_lo));
     CU(cudaMemsetAsync(&dc->n_rays[0], 0, 2 * sizeof(uint32_t), st));
     launch_raygen(fp, slot_lo, slot_hi, ray_queue(S, 0), &dc->n_rays[0], st);
     ++launches;
-    bool first_wave = true;
-    for (uint32_t depth = 0;; ++depth) {
-      CU(cudaMemcpyAsync(&S.h_counters->n_rays[cur], &dc->n_rays[cur], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      uint32_t n = S.h_counters->n_rays[cur];
-      if (first_wave) primary += n, first_wave = false;
-      if (n == 0) break;
-      ++waves;
-      // capacities for this wave
-      uint64_t next_need = (uint64_t)n * (uint64_t)S.child_factor;
+
+    // Pipelined waves.  Wave k consumes queue k%2 holding n_k rays; n_k is written by shade of wave
+    // k-1.  All kernels read their counts from device memory, so wave k is enqueued as soon as the
+    // host knows n_{k-1} (bound: n_k <= child_factor * n_{k-1}) — i.e. while wave k-1 still runs.
+    std::vector<cudaEvent_t> count_ev;
+    size_t wave_base = wave_counts_used;
+    uint64_t known_prev = n0;  // n_{k-1} (exact) when enqueuing wave k; for k == 0 it is n_0 itself
+    for (uint32_t k = 0; k < fp.max_depth; ++k) {
+      int cur = (int)(k & 1u);
+      uint64_t bound;
+      if (k == 0) {
+        bound = n0;
+      } else {
+        if (k >= 2) {
+          CU(cudaEventSynchronize(count_ev[k - 1]));
+          known_prev = S.h_wave_counts[wave_base + k - 1];
+        }
+        if (known_prev == 0 || S.child_factor == 0) break;
+        bound = known_prev * (uint64_t)S.child_factor;
+      }
+      // this wave's exact count arrives in pinned memory once the producer finished (k >= 1)
+      if (wave_base + k >= S.h_wave_cap) return fail(NRB_ERR_INVALID_ARG, "max_depth too large for the wave-count buffer");
+      if (k == 0) {
+        S.h_wave_counts[wave_base] = (uint32_t)n0;
+        count_ev.push_back(nullptr);
+      } else {
+        CU(cudaMemcpyAsync(&S.h_wave_counts[wave_base + k], &dc->n_rays[cur], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        cudaEvent_t ev = get_event(S, ev_used);
+        CU(cudaEventRecord(ev, st));
+        count_ev.push_back(ev);
+      }
+      ++wave_counts_used;
+      uint64_t next_need = bound * (uint64_t)S.child_factor;
       if (next_need * 48 > mem_ceiling || next_need >= (1ull << 32))
         return fail(NRB_ERR_QUEUE_OVERFLOW, "secondary-ray queue would exceed NRB_QUEUE_BYTES");
       CU(ensure_ray_queue(S, 1 - cur, (uint32_t)next_need));
-      if (n > S.hits_cap) {
-        CU(S.d_hits.ensure((size_t)n * 16));
-        S.hits_cap = n;
+      if (bound > S.hits_cap) {
+        // growing a buffer frees the old one: drain the stream first (rare: first frames only)
+        CU(cudaStreamSynchronize(st));
+        CU(S.d_hits.ensure((size_t)bound * 16));
+        S.hits_cap = (uint32_t)bound;
       }
-      uint32_t chunk = n;
+      uint32_t n_exact_or_bound = (uint32_t)bound;
+      uint32_t chunk = n_exact_or_bound;
       if (S_total) {
-        uint64_t want = std::min<uint64_t>((uint64_t)n * S_total, std::max<uint64_t>(shadow_cap_req, S_total));
+        uint64_t want = bound * S_total;
+        if (want > std::max<uint64_t>(shadow_cap_req, S_total)) {
+          // shadow rays of this wave may not fit: fall back to the exact count and chunk the wave
+          if (k >= 1) {
+            CU(cudaEventSynchronize(count_ev[k]));
+            n_exact_or_bound = S.h_wave_counts[wave_base + k];
+          }
+          want = std::min<uint64_t>((uint64_t)n_exact_or_bound * S_total, std::max<uint64_t>(shadow_cap_req, S_total));
+        }
         if (want > S.sq_cap) {
+          CU(cudaStreamSynchronize(st));
           for (int c = 0; c < 3; ++c) CU(S.d_sq[c].ensure((size_t)want * 16));
           S.sq_cap = (uint32_t)want;
         }
-        chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n, S.sq_cap / S_total));
+        chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_exact_or_bound, S.sq_cap / S_total));
       }
+      if (n_exact_or_bound == 0) break;
       ShadowQueue sq{S.d_sq[0].as<float4>(), S.d_sq[1].as<float4>(), S.d_sq[2].as<float4>(), S.sq_cap};
       CU(cudaMemsetAsync(&dc->n_rays[1 - cur], 0, sizeof(uint32_t), st));
       CU(cudaMemsetAsync(&dc->fetch_closest, 0, sizeof(uint32_t), st));
@@ -609,11 +670,20 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
       closest_spans.emplace_back(e0, e1);
       ++launches;
       // K4 shade (+ K3 shadow) in chunks bounded by the shadow queue
-      for (uint32_t lo = 0; lo < n; lo += chunk) {
-        uint32_t hi = std::min<uint64_t>(n, (uint64_t)lo + chunk);
+      for (uint32_t lo = 0; lo < n_exact_or_bound; lo += chunk) {
+        uint32_t hi = (uint32_t)std::min<uint64_t>(n_exact_or_bound, (uint64_t)lo + chunk);
         if (S_total) CU(cudaMemsetAsync(&dc->n_shadow, 0, sizeof(uint32_t), st));
-        launch_shade(S.view, S.has_shapes, fp, ray_queue(S, cur), S.d_hits.as<float4>(), lo, hi, ray_queue(S, 1 - cur),
-                     &dc->n_rays[1 - cur], sq, dc, accum, st);
+        cudaEvent_t h0 = nullptr, h1 = nullptr;
+        if (dump) {
+          h0 = get_event(S, ev_used), h1 = get_event(S, ev_used);
+          CU(cudaEventRecord(h0, st));
+        }
+        launch_shade(S.view, S.has_shapes, fp, ray_queue(S, cur), S.d_hits.as<float4>(), &dc->n_rays[cur], lo, hi,
+                     ray_queue(S, 1 - cur), &dc->n_rays[1 - cur], sq, dc, accum, S.grid_shade, st);
+        if (dump) {
+          CU(cudaEventRecord(h1, st));
+          shade_spans.emplace_back(h0, h1);
+        }
         ++launches;
         if (S_total) {
           CU(cudaMemsetAsync(&dc->fetch_shadow, 0, sizeof(uint32_t), st));
@@ -625,7 +695,6 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
           ++launches;
         }
       }
-      cur = 1 - cur;
     }
   }
   if (d_out8)
@@ -637,6 +706,20 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   CU(cudaMemcpyAsync(S.h_counters, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
+  for (size_t i = 0; i < wave_counts_used; ++i) waves += S.h_wave_counts[i] ? 1u : 0u;
+  if (dump) {
+    float total = 0.0f;
+    cudaEventElapsedTime(&total, S.ev_begin, S.ev_end);
+    fprintf(stderr, "[nrb] frame %.3f ms, %zu waves enqueued\n", total, wave_counts_used);
+    for (size_t i = 0; i < wave_counts_used; ++i) {
+      float tc = 0, th = 0, ts = 0, t0 = 0;
+      if (i < closest_spans.size()) cudaEventElapsedTime(&tc, closest_spans[i].first, closest_spans[i].second);
+      if (i < shade_spans.size()) cudaEventElapsedTime(&th, shade_spans[i].first, shade_spans[i].second);
+      if (i < shadow_spans.size()) cudaEventElapsedTime(&ts, shadow_spans[i].first, shadow_spans[i].second);
+      if (i < closest_spans.size()) cudaEventElapsedTime(&t0, S.ev_begin, closest_spans[i].first);
+      fprintf(stderr, "[nrb]  wave %2zu n=%9u start=%.3f closest=%.3f shade=%.3f shadow=%.3f\n", i, S.h_wave_counts[i], t0, tc, th, ts);
+    }
+  }
   if (S.h_counters->overflow) return fail(NRB_ERR_QUEUE_OVERFLOW, "a device queue overflowed (internal capacity bug)");
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
@@ -718,6 +801,7 @@ int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out) {
   if (rc) return rc;
   S->grid_closest = S->sm_count * trace_blocks_per_sm(S->has_shapes, false);
   S->grid_shadow = S->sm_count * trace_blocks_per_sm(S->has_shapes, true);
+  S->grid_shade = S->sm_count * shade_blocks_per_sm(S->has_shapes);
   *out = S.release();
   return NRB_OK;
 }

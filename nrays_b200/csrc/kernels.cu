@@ -395,156 +395,214 @@ __global__ void __launch_bounds__(kTraceBlock) trace_shadow_kernel(SceneView sc,
 // ---------------------------------------------------------------------------------------------
 // K4 — shade + secondary-ray generation (Scene::trace body after the cast, src/scene.rs:168-192)
 // ---------------------------------------------------------------------------------------------
+// Persistent grid; the ray count is read from device memory so the host can enqueue a wave without
+// knowing how many rays the previous one produced.  Queue slots are reserved per BLOCK (warp totals
+// meet in shared memory, one global atomic per block per queue and iteration) and the ray statistics
+// live in registers until the kernel ends: same-address global atomics would otherwise serialise in L2.
+struct ShadeShared {
+  uint32_t cnt[2];   // [0] shadow entries, [1] secondary rays requested by this block in this iteration
+  uint32_t base[2];  // their first slots in the global queues
+};
+
 template <bool HAS_SHAPES>
-__global__ void __launch_bounds__(kShadeBlock) shade_kernel(SceneView sc, FrameParams fp, RayQueue qin,
-                                                           const float4 *hits, uint32_t lo, uint32_t hi,
-                                                           RayQueue qout, uint32_t *tail_out, ShadowQueue sq,
-                                                           Counters *ctr, float4 *accum) {
-  uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
-  bool active = i < hi;
-  float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra, h = ra;
-  if (active) {
-    ra = qin.a[i], rb = qin.b[i], rc = qin.c[i];
-    h = hits[i];
-  }
-  V3 o = mk(ra.x, ra.y, ra.z), d = mk(ra.w, rb.x, rb.y);
-  float weight = rb.z, energy = rb.w, refr = rc.x;
-  uint32_t gid = __float_as_uint(rc.y), path = __float_as_uint(rc.z), depth = __float_as_uint(rc.w);
-  uint32_t prim = __float_as_uint(h.y);
-  uint32_t ipt = gid / fp.spp, smp = gid - ipt * fp.spp;
-  uint32_t pix = active ? accum_index(fp, ipt) : 0u;
+__global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(SceneView sc, FrameParams fp, RayQueue qin,
+                                                                            const float4 *hits,
+                                                                            const uint32_t *count_ptr, uint32_t lo,
+                                                                            uint32_t hi, RayQueue qout,
+                                                                            uint32_t *tail_out, ShadowQueue sq,
+                                                                            Counters *ctr, float4 *accum) {
+  __shared__ ShadeShared sm;
+  if (threadIdx.x < 2) sm.cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t end = min(hi, *count_ptr);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t lane = lane_id();
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t c_shadow = 0, c_refl = 0, c_refr = 0, c_trunc = 0;
 
-  bool is_hit = active && prim != kMiss;
-  if (active && !is_hit) {
-    // miss -> background (src/scene.rs:169)
-    accum_add(accum, pix, mk(sc.background[0], sc.background[1], sc.background[2]) * weight);
-  }
-
-  // ---- hit: reconstruct the intersection, evaluate the material --------------------------------
-  Surface s;
-  s.n = mk(0, 0, 1), s.u = s.v = 0.0f, s.has_uv = false, s.node = 0;
-  V3 pt = mk(0, 0, 0);
-  NodeInfo ni;
-  ni.material = 0, ni.refl_mix = 0, ni.refl_att = 0, ni.alpha = 1, ni.refr_coeff = 1, ni.flags = 0;
-  Material m;
-  m.kind = NRB_MAT_NORMAL;
-  float4 tex_color = make_float4(1, 1, 1, 1);
-  float obj_w = 1.0f;
-  V3 obj_rgb = mk(0, 0, 0);
-  bool phong = false;
-  if (is_hit) {
-    reconstruct<HAS_SHAPES>(sc, o, d, prim, h.z, h.w, s);
-    pt = o + d * h.x;
-    ni = sc.node_info[s.node];
-    m = sc.materials[ni.material];
-    if (m.kind == NRB_MAT_PHONG) {
-      // PhongMaterial::compute, ambient part (src/phong_material.rs:85-103)
-      phong = true;
-      if (s.has_uv && m.tex >= 0) tex_color = tex_sample(sc, m.tex, s.u, s.v);
-      if (s.has_uv && m.alpha_tex >= 0) obj_w = tex_sample(sc, m.alpha_tex, s.u, s.v).w;
-      obj_rgb = mk(m.ambient[0] * tex_color.x, m.ambient[1] * tex_color.y, m.ambient[2] * tex_color.z);
-    } else {
-      float4 c = mat_ambiant(sc, m, s);  // Material::compute default (src/material.rs:8-16)
-      obj_rgb = mk(c.x, c.y, c.z);
-      obj_w = c.w;
+  for (uint32_t bb = lo + blockIdx.x * blockDim.x; bb < end; bb += stride) {  // block-uniform trip count
+    const uint32_t i = bb + threadIdx.x;
+    const bool active = i < end;
+    float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra, h = ra;
+    if (active) {
+      ra = qin.a[i], rb = qin.b[i], rc = qin.c[i];
+      h = hits[i];
     }
-  }
-  // combine weights (src/scene.rs:178-190): out = alpha==1 ? col : col*alpha + refr*(1-alpha),
-  // col = obj*(1-mix) + refl*mix
-  float alpha = obj_w * ni.alpha;
-  float a1 = (alpha == 1.0f) ? 1.0f : alpha;
-  float w_obj = weight * a1 * (1.0f - ni.refl_mix);
-  if (is_hit) accum_add(accum, pix, obj_rgb * w_obj);
+    V3 o = mk(ra.x, ra.y, ra.z), d = mk(ra.w, rb.x, rb.y);
+    float weight = rb.z, energy = rb.w, refr = rc.x;
+    uint32_t gid = __float_as_uint(rc.y), path = __float_as_uint(rc.z), depth = __float_as_uint(rc.w);
+    uint32_t prim = __float_as_uint(h.y);
+    uint32_t ipt = gid / fp.spp, smp = gid - ipt * fp.spp;
+    uint32_t pix = active ? accum_index(fp, ipt) : 0u;
 
-  // ---- light samples -> shadow rays (src/phong_material.rs:106-147, src/light.rs:56-63) --------
-  uint32_t n_sh = (is_hit && phong) ? (uint32_t)sc.shadow_samples : 0u;
-  uint32_t sbase = warp_append_n(&ctr->n_shadow, n_sh, &ctr->rays_shadow);
-  if (n_sh) {
-    uint32_t k_out = 0;
-    for (int li = 0; li < sc.n_lights; ++li) {
-      const Light L = sc.lights[li];
-      uint32_t ns = L.racsample * L.racsample;
-      float inv_ns = 1.0f / (float)ns;
-      for (uint32_t k = 0; k < ns; ++k, ++k_out) {
-        V3 pos = mk(L.pos[0], L.pos[1], L.pos[2]);
-        if (L.radius != 0.0f) {
-          uint32_t rnd[4];
-          philox4x32_10(ipt, smp, path, ((uint32_t)li << 16) | (k & 0xFFFFu), fp.seed_lo, fp.seed_hi ^ kStreamLight, rnd);
-          pos = pos + mk(u24(rnd[0]), u24(rnd[1]), u24(rnd[2])) * L.radius;
-        }
-        V3 ldir = pos - pt;
-        float len = sqrtf(dot(ldir, ldir));
-        ldir = ldir * (1.0f / len);
-        float dist = len - 0.001f;
-        float ndl = dot(ldir, s.n);
-        float dcoeff = fmaxf(ndl, 0.0f);
-        V3 diffuse = mk(m.diffuse[0] * tex_color.x, m.diffuse[1] * tex_color.y, m.diffuse[2] * tex_color.z) * dcoeff;
-        V3 rl = normalize(-ldir + s.n * (2.0f * ndl));
-        float scoeff = -dot(rl, d);
-        V3 c = diffuse;
-        if (scoeff > 0.0f) {
-          float sp = powf(scoeff, m.shininess);
-          c = c + mk(m.specular[0], m.specular[1], m.specular[2]) * sp;
-        }
-        c = cmul(mk(L.color[0], L.color[1], L.color[2]), c) * (inv_ns * w_obj);
-        uint32_t si = sbase + k_out;
-        if (si < sq.capacity) {
-          V3 so = pt + ldir * 0.001f;
-          sq.a[si] = make_float4(so.x, so.y, so.z, dist);
-          sq.b[si] = make_float4(ldir.x, ldir.y, ldir.z, __uint_as_float(pix));
-          sq.c[si] = make_float4(c.x, c.y, c.z, 0.0f);
-        } else {
-          ctr->overflow = 1u;
-        }
-      }
+    bool is_hit = active && prim != kMiss;
+    if (active && !is_hit) {
+      // miss -> background (src/scene.rs:169)
+      accum_add(accum, pix, mk(sc.background[0], sc.background[1], sc.background[2]) * weight);
     }
-  }
 
-  // ---- reflection (Scene::trace_reflection, src/scene.rs:196-218) ------------------------------
-  bool want_refl = is_hit && ni.refl_mix != 0.0f && energy > 0.1f;
-  bool trunc_refl = want_refl && (depth + 1u >= fp.max_depth);
-  want_refl = want_refl && !trunc_refl;
-  // ---- refraction (Scene::trace_refraction, src/scene.rs:221-252) ------------------------------
-  bool want_refr = is_hit && alpha != 1.0f;
-  bool trunc_refr = want_refr && (depth + 1u >= fp.max_depth);
-  want_refr = want_refr && !trunc_refr;
-  count_warp(&ctr->paths_truncated, trunc_refl);
-  count_warp(&ctr->paths_truncated, trunc_refr);
-  count_warp(&ctr->rays_reflect, want_refl);
-  count_warp(&ctr->rays_refract, want_refr);
-
-  uint32_t ri = warp_append(tail_out, want_refl);
-  if (want_refl) {
-    if (ri < qout.capacity) {
-      float dn = dot(d, s.n);
-      V3 rdir = d - s.n * (2.0f * dn);
-      V3 ro = pt + rdir * 0.001f;
-      qout.a[ri] = make_float4(ro.x, ro.y, ro.z, rdir.x);
-      qout.b[ri] = make_float4(rdir.y, rdir.z, weight * a1 * ni.refl_mix, energy - ni.refl_att);
-      qout.c[ri] = make_float4(refr, __uint_as_float(gid), __uint_as_float(path * 2u), __uint_as_float(depth + 1u));
-    } else {
-      ctr->overflow = 1u;
-    }
-  }
-  uint32_t fi = warp_append(tail_out, want_refr);
-  if (want_refr) {
-    if (fi < qout.capacity) {
-      float n1, n2;
-      if (refr == 1.0f) {
-        n1 = 1.0f, n2 = ni.refr_coeff;
+    // ---- hit: reconstruct the intersection, evaluate the material ------------------------------
+    Surface s;
+    s.n = mk(0, 0, 1), s.u = s.v = 0.0f, s.has_uv = false, s.node = 0;
+    V3 pt = mk(0, 0, 0);
+    NodeInfo ni;
+    ni.material = 0, ni.refl_mix = 0, ni.refl_att = 0, ni.alpha = 1, ni.refr_coeff = 1, ni.flags = 0;
+    Material m;
+    m.kind = NRB_MAT_NORMAL;
+    float4 tex_color = make_float4(1, 1, 1, 1);
+    float obj_w = 1.0f;
+    V3 obj_rgb = mk(0, 0, 0);
+    bool phong = false;
+    if (is_hit) {
+      reconstruct<HAS_SHAPES>(sc, o, d, prim, h.z, h.w, s);
+      pt = o + d * h.x;
+      ni = sc.node_info[s.node];
+      m = sc.materials[ni.material];
+      if (m.kind == NRB_MAT_PHONG) {
+        // PhongMaterial::compute, ambient part (src/phong_material.rs:85-103)
+        phong = true;
+        if (s.has_uv && m.tex >= 0) tex_color = tex_sample(sc, m.tex, s.u, s.v);
+        if (s.has_uv && m.alpha_tex >= 0) obj_w = tex_sample(sc, m.alpha_tex, s.u, s.v).w;
+        obj_rgb = mk(m.ambient[0] * tex_color.x, m.ambient[1] * tex_color.y, m.ambient[2] * tex_color.z);
       } else {
-        n1 = ni.refr_coeff, n2 = 1.0f;
+        float4 c = mat_ambiant(sc, m, s);  // Material::compute default (src/material.rs:8-16)
+        obj_rgb = mk(c.x, c.y, c.z);
+        obj_w = c.w;
       }
-      V3 along = s.n * dot(d, s.n);
-      V3 tangent = d - along;
-      V3 nd = normalize(along + tangent * (n2 / n1));
-      V3 no = pt + nd * 0.001f;
-      qout.a[fi] = make_float4(no.x, no.y, no.z, nd.x);
-      qout.b[fi] = make_float4(nd.y, nd.z, weight * (1.0f - alpha), energy);
-      qout.c[fi] = make_float4(n2, __uint_as_float(gid), __uint_as_float(path * 2u + 1u), __uint_as_float(depth + 1u));
-    } else {
-      ctr->overflow = 1u;
     }
+    // combine weights (src/scene.rs:178-190): out = alpha==1 ? col : col*alpha + refr*(1-alpha),
+    // col = obj*(1-mix) + refl*mix
+    float alpha = obj_w * ni.alpha;
+    float a1 = (alpha == 1.0f) ? 1.0f : alpha;
+    float w_obj = weight * a1 * (1.0f - ni.refl_mix);
+    if (is_hit) accum_add(accum, pix, obj_rgb * w_obj);
+
+    // ---- what this ray emits ------------------------------------------------------------------
+    const bool emit_sh = is_hit && phong && sc.shadow_samples > 0;
+    // reflection (Scene::trace_reflection, src/scene.rs:196-218)
+    bool want_refl = is_hit && ni.refl_mix != 0.0f && energy > 0.1f;
+    const bool trunc_refl = want_refl && (depth + 1u >= fp.max_depth);
+    want_refl = want_refl && !trunc_refl;
+    // refraction (Scene::trace_refraction, src/scene.rs:221-252)
+    bool want_refr = is_hit && alpha != 1.0f;
+    const bool trunc_refr = want_refr && (depth + 1u >= fp.max_depth);
+    want_refr = want_refr && !trunc_refr;
+    c_trunc += (trunc_refl ? 1u : 0u) + (trunc_refr ? 1u : 0u);
+    c_refl += want_refl ? 1u : 0u;
+    c_refr += want_refr ? 1u : 0u;
+    c_shadow += emit_sh ? (uint32_t)sc.shadow_samples : 0u;
+
+    // ---- reserve queue slots: warp ballots -> shared-memory totals -> one global atomic per block ----
+    const uint32_t m_sh = __ballot_sync(0xFFFFFFFFu, emit_sh);
+    const uint32_t m_rl = __ballot_sync(0xFFFFFFFFu, want_refl);
+    const uint32_t m_rr = __ballot_sync(0xFFFFFFFFu, want_refr);
+    uint32_t woff_sh = 0, woff_ch = 0;
+    if (lane == 0) {
+      uint32_t tsh = __popc(m_sh) * (uint32_t)sc.shadow_samples, tch = __popc(m_rl) + __popc(m_rr);
+      if (tsh) woff_sh = atomicAdd(&sm.cnt[0], tsh);
+      if (tch) woff_ch = atomicAdd(&sm.cnt[1], tch);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = sm.cnt[0];
+      sm.base[0] = t ? atomicAdd(&ctr->n_shadow, t) : 0u;
+      sm.cnt[0] = 0;
+    } else if (threadIdx.x == 32) {
+      uint32_t t = sm.cnt[1];
+      sm.base[1] = t ? atomicAdd(tail_out, t) : 0u;
+      sm.cnt[1] = 0;
+    }
+    __syncthreads();
+    const uint32_t sbase = sm.base[0] + __shfl_sync(0xFFFFFFFFu, woff_sh, 0) + __popc(m_sh & lt_mask) * (uint32_t)sc.shadow_samples;
+    const uint32_t cbase = sm.base[1] + __shfl_sync(0xFFFFFFFFu, woff_ch, 0) + __popc(m_rl & lt_mask) + __popc(m_rr & lt_mask);
+
+    // ---- light samples -> shadow rays (src/phong_material.rs:106-147, src/light.rs:56-63) ------
+    if (emit_sh) {
+      uint32_t k_out = 0;
+      for (int li = 0; li < sc.n_lights; ++li) {
+        const Light L = sc.lights[li];
+        uint32_t ns = L.racsample * L.racsample;
+        float inv_ns = 1.0f / (float)ns;
+        for (uint32_t k = 0; k < ns; ++k, ++k_out) {
+          V3 pos = mk(L.pos[0], L.pos[1], L.pos[2]);
+          if (L.radius != 0.0f) {
+            uint32_t rnd[4];
+            philox4x32_10(ipt, smp, path, ((uint32_t)li << 16) | (k & 0xFFFFu), fp.seed_lo, fp.seed_hi ^ kStreamLight, rnd);
+            pos = pos + mk(u24(rnd[0]), u24(rnd[1]), u24(rnd[2])) * L.radius;
+          }
+          V3 ldir = pos - pt;
+          float len = sqrtf(dot(ldir, ldir));
+          ldir = ldir * (1.0f / len);
+          float dist = len - 0.001f;
+          float ndl = dot(ldir, s.n);
+          float dcoeff = fmaxf(ndl, 0.0f);
+          V3 diffuse = mk(m.diffuse[0] * tex_color.x, m.diffuse[1] * tex_color.y, m.diffuse[2] * tex_color.z) * dcoeff;
+          V3 rl = normalize(-ldir + s.n * (2.0f * ndl));
+          float scoeff = -dot(rl, d);
+          V3 c = diffuse;
+          if (scoeff > 0.0f) {
+            float sp = powf(scoeff, m.shininess);
+            c = c + mk(m.specular[0], m.specular[1], m.specular[2]) * sp;
+          }
+          c = cmul(mk(L.color[0], L.color[1], L.color[2]), c) * (inv_ns * w_obj);
+          uint32_t si = sbase + k_out;
+          if (si < sq.capacity) {
+            V3 so = pt + ldir * 0.001f;
+            sq.a[si] = make_float4(so.x, so.y, so.z, dist);
+            sq.b[si] = make_float4(ldir.x, ldir.y, ldir.z, __uint_as_float(pix));
+            sq.c[si] = make_float4(c.x, c.y, c.z, 0.0f);
+          } else {
+            ctr->overflow = 1u;
+          }
+        }
+      }
+    }
+
+    if (want_refl) {
+      uint32_t ri = cbase;
+      if (ri < qout.capacity) {
+        float dn = dot(d, s.n);
+        V3 rdir = d - s.n * (2.0f * dn);
+        V3 ro = pt + rdir * 0.001f;
+        qout.a[ri] = make_float4(ro.x, ro.y, ro.z, rdir.x);
+        qout.b[ri] = make_float4(rdir.y, rdir.z, weight * a1 * ni.refl_mix, energy - ni.refl_att);
+        qout.c[ri] = make_float4(refr, __uint_as_float(gid), __uint_as_float(path * 2u), __uint_as_float(depth + 1u));
+      } else {
+        ctr->overflow = 1u;
+      }
+    }
+    if (want_refr) {
+      uint32_t fi = cbase + (want_refl ? 1u : 0u);
+      if (fi < qout.capacity) {
+        float n1, n2;
+        if (refr == 1.0f) {
+          n1 = 1.0f, n2 = ni.refr_coeff;
+        } else {
+          n1 = ni.refr_coeff, n2 = 1.0f;
+        }
+        V3 along = s.n * dot(d, s.n);
+        V3 tangent = d - along;
+        V3 nd = normalize(along + tangent * (n2 / n1));
+        V3 no = pt + nd * 0.001f;
+        qout.a[fi] = make_float4(no.x, no.y, no.z, nd.x);
+        qout.b[fi] = make_float4(nd.y, nd.z, weight * (1.0f - alpha), energy);
+        qout.c[fi] = make_float4(n2, __uint_as_float(gid), __uint_as_float(path * 2u + 1u), __uint_as_float(depth + 1u));
+      } else {
+        ctr->overflow = 1u;
+      }
+    }
+  }
+
+  // ---- flush the register statistics: one atomic per warp and counter ----
+  c_shadow = __reduce_add_sync(0xFFFFFFFFu, c_shadow);
+  c_refl = __reduce_add_sync(0xFFFFFFFFu, c_refl);
+  c_refr = __reduce_add_sync(0xFFFFFFFFu, c_refr);
+  c_trunc = __reduce_add_sync(0xFFFFFFFFu, c_trunc);
+  if (lane == 0) {
+    if (c_shadow) atomicAdd(&ctr->rays_shadow, (unsigned long long)c_shadow);
+    if (c_refl) atomicAdd(&ctr->rays_reflect, (unsigned long long)c_refl);
+    if (c_refr) atomicAdd(&ctr->rays_refract, (unsigned long long)c_refr);
+    if (c_trunc) atomicAdd(&ctr->paths_truncated, (unsigned long long)c_trunc);
   }
 }
 
@@ -613,15 +671,22 @@ void launch_trace_shadow(const SceneView &sc, bool has_shapes, ShadowQueue q, fl
 }
 
 void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, RayQueue qin, const float4 *hits,
-                  uint32_t lo, uint32_t hi, RayQueue qout, uint32_t *tail_out, ShadowQueue sq, Counters *ctr,
-                  float4 *accum, cudaStream_t st) {
-  uint32_t n = hi - lo;
-  if (!n) return;
-  uint32_t grid = (n + kShadeBlock - 1) / kShadeBlock;
+                  const uint32_t *count, uint32_t lo, uint32_t hi, RayQueue qout, uint32_t *tail_out, ShadowQueue sq,
+                  Counters *ctr, float4 *accum, int grid, cudaStream_t st) {
+  if (hi <= lo) return;
   if (has_shapes)
-    shade_kernel<true><<<grid, kShadeBlock, 0, st>>>(sc, fp, qin, hits, lo, hi, qout, tail_out, sq, ctr, accum);
+    shade_kernel<true><<<grid, kShadeBlock, 0, st>>>(sc, fp, qin, hits, count, lo, hi, qout, tail_out, sq, ctr, accum);
   else
-    shade_kernel<false><<<grid, kShadeBlock, 0, st>>>(sc, fp, qin, hits, lo, hi, qout, tail_out, sq, ctr, accum);
+    shade_kernel<false><<<grid, kShadeBlock, 0, st>>>(sc, fp, qin, hits, count, lo, hi, qout, tail_out, sq, ctr, accum);
+}
+
+int shade_blocks_per_sm(bool has_shapes) {
+  int nb = 0;
+  if (has_shapes)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, shade_kernel<true>, kShadeBlock, 0);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, shade_kernel<false>, kShadeBlock, 0);
+  return nb > 0 ? nb : 1;
 }
 
 void launch_resolve(const float4 *accum, uint32_t n, uint32_t spp, float *out_rgb, cudaStream_t st) {
