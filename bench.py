@@ -273,15 +273,15 @@ def run_ours(args, rank, local_rank, world):
         geom_bytes = s0["bvh_nodes"] * 64 + s0["triangles"] * 48
         n_closest = sum(s["rays_primary"] + s["rays_reflect"] + s["rays_refract"] for s, _ in stats_dev)
         n_shadow = sum(s["rays_shadow"] for s, _ in stats_dev)
-        ms_closest = sum(s["ms_closest"] for s, _ in stats_dev)
-        ms_shadow = sum(s["ms_shadow"] for s, _ in stats_dev)
-        l_closest = sum(s["launches_closest"] for s, _ in stats_dev)
-        l_shadow = sum(s["launches_shadow"] for s, _ in stats_dev)
-        if ms_closest >= ms_shadow:
-            kname, rays_k, ms_k, l_k, per_ray = "trace_closest_kernel", n_closest, ms_closest, l_closest, 48
-        else:
-            kname, rays_k, ms_k, l_k, per_ray = "trace_shadow_kernel", n_shadow, ms_shadow, l_shadow, 64
-        bytes_k = rays_k * per_ray + l_k * geom_bytes
+        # dominant kernel: the persistent trace kernel (closest hits read 32 B of ray + write a 16 B hit
+        # record; wave 0 generates its rays on chip: 16 B; shadow rays read 48 B + one 16 B RED)
+        ms_k = sum(s["ms_trace"] for s, _ in stats_dev)
+        l_k = sum(s["launches_trace"] for s, _ in stats_dev)
+        kname = "trace_kernel"
+        n_primary_k = sum(s["rays_primary"] for s, _ in stats_dev)
+        rays_k = n_closest + n_shadow
+        per_ray = None
+        bytes_k = 16 * n_primary_k + 48 * (n_closest - n_primary_k) + 64 * n_shadow + l_k * geom_bytes
         achieved = bytes_k / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
         n_primary = sum(s["rays_primary"] for s, _ in stats_dev)
         frame_bytes = 160 * (n_closest + n_shadow) + 16 * n_primary + len(stats_dev) * s0["scene_bytes"]

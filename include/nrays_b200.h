@@ -167,16 +167,15 @@ typedef struct NrbStats {
   uint32_t waves;           /* wavefront iterations */
   uint32_t kernel_launches; /* this library's kernels launched by the call */
   float ms_device;          /* CUDA-event span raygen -> resolve on the render stream */
-  float ms_trace;           /* sum of closest-hit + shadow traversal kernels */
-  float ms_shade;           /* sum of raygen + shade + resolve kernels */
+  float ms_trace;           /* CUDA-event time of the trace kernel launches (closest hit + shadow rays) */
+  float ms_shade;           /* ms_device - ms_trace: shade + resolve + inter-kernel gaps */
   uint32_t _pad;
   uint64_t bvh_nodes;       /* device BVH size, for the roofline's scene_bytes */
   uint64_t triangles;
   uint64_t scene_bytes;
-  float ms_closest;         /* CUDA-event time of the closest-hit traversal launches */
-  float ms_shadow;          /* CUDA-event time of the shadow traversal launches */
-  uint32_t launches_closest;
-  uint32_t launches_shadow;
+  uint32_t launches_trace;  /* launches of the persistent trace kernel (ms_trace is their CUDA-event time) */
+  uint32_t launches_shade;  /* launches of the shade kernel */
+  uint32_t _reserved[2];
 } NrbStats;
 
 typedef struct NrbScene NrbScene; /* opaque handle == Arc<Scene> of the reference */

@@ -141,10 +141,9 @@ class NrbStats(C.Structure):
         ("bvh_nodes", C.c_uint64),
         ("triangles", C.c_uint64),
         ("scene_bytes", C.c_uint64),
-        ("ms_closest", C.c_float),
-        ("ms_shadow", C.c_float),
-        ("launches_closest", C.c_uint32),
-        ("launches_shadow", C.c_uint32),
+        ("launches_trace", C.c_uint32),
+        ("launches_shade", C.c_uint32),
+        ("_reserved", C.c_uint32 * 2),
     ]
 
     @property

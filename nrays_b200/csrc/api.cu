@@ -83,9 +83,9 @@ struct NrbScene {
   bool has_shapes = false;
   int child_factor = 0;  // max secondary rays per ray (reflection + refraction possible in this scene)
   uint64_t n_bvh_nodes = 0, n_tris = 0, scene_bytes = 0;
-  int grid_closest = 148, grid_shadow = 148;
+  int grid_trace = 148;
   // frame state
-  DevBuf d_q[2][3], d_hits, d_sq[3], d_accum, d_counters, d_out, d_out8;
+  DevBuf d_q[2][3], d_hits, d_sq[3], d_accum, d_counters, d_wave, d_out, d_out8;
   uint32_t q_cap[2] = {0, 0}, sq_cap = 0, hits_cap = 0;
   Counters *h_counters = nullptr;  // pinned mirror
   uint32_t *h_wave_counts = nullptr;  // pinned: exact ray count of every wave of the current frame
@@ -552,7 +552,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   uint32_t launches = 0, waves = 0;
   size_t wave_counts_used = 0;
   size_t ev_used = 0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> closest_spans, shadow_spans, shade_spans;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_spans, shade_spans;
   const bool dump = getenv("NRB_DUMP_WAVES") != nullptr;
 
   {
@@ -580,9 +580,14 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   const uint32_t S_total = (uint32_t)S.view.shadow_samples;
   uint64_t primary = 0;
 
+  const size_t wc_len = (size_t)fp.max_depth + 3;
+  CU(S.d_wave.ensure(wc_len * sizeof(WaveCounters)));
+  WaveCounters *wc = S.d_wave.as<WaveCounters>();
+  const RayQueue no_queue{nullptr, nullptr, nullptr, 0};
+
   for (uint64_t tile_lo = 0; tile_lo < fp.n_local_tiles; tile_lo += tiles_per_batch) {
     uint64_t tile_hi = std::min<uint64_t>(fp.n_local_tiles, tile_lo + tiles_per_batch);
-    uint32_t slot_lo = (uint32_t)(tile_lo * per_tile), slot_hi = (uint32_t)(tile_hi * per_tile);
+    const uint32_t slot_lo = (uint32_t)(tile_lo * per_tile), n_slots = (uint32_t)((tile_hi - tile_lo) * per_tile);
     // exact number of primary rays of this batch (samples of pixels inside the image): no sync needed
     uint64_t n0 = 0;
     for (uint64_t lt = tile_lo; lt < tile_hi; ++lt) {
@@ -592,22 +597,33 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
       n0 += (uint64_t)wpx * hpx * fp.spp;
     }
     primary += n0;
-    CU(ensure_ray_queue(S, 0, slot_hi - slot_lo));
-    CU(cudaMemsetAsync(&dc->n_rays[0], 0, 2 * sizeof(uint32_t), st));
-    launch_raygen(fp, slot_lo, slot_hi, ray_queue(S, 0), &dc->n_rays[0], st);
-    ++launches;
+    CU(cudaMemsetAsync(wc, 0, wc_len * sizeof(WaveCounters), st));  // the only counter reset of the batch
 
-    // Pipelined waves.  Wave k consumes queue k%2 holding n_k rays; n_k is written by shade of wave
-    // k-1.  All kernels read their counts from device memory, so wave k is enqueued as soon as the
-    // host knows n_{k-1} (bound: n_k <= child_factor * n_{k-1}) — i.e. while wave k-1 still runs.
+    // Pipelined waves.  Wave k >= 1 consumes queue k%2 holding n_k = wc[k].n_rays rays (written by the
+    // shade of wave k-1); wave 0 generates its rays from the sample slots.  Every kernel reads its
+    // counts from device memory, so wave k is enqueued as soon as the host knows n_{k-1}
+    // (n_k <= child_factor * n_{k-1}) — i.e. while wave k-1 is still running.
+    // Per wave: ONE trace launch (shadow rays of wave k-1 + closest hits of wave k) and ONE shade launch.
     std::vector<cudaEvent_t> count_ev;
-    size_t wave_base = wave_counts_used;
-    uint64_t known_prev = n0;  // n_{k-1} (exact) when enqueuing wave k; for k == 0 it is n_0 itself
+    const size_t wave_base = wave_counts_used;
+    uint64_t known_prev = n0;
+    int pending_shadow = -1;  // wave whose shadow queue has not been traced yet
+    auto trace_span = [&](bool primary, RayQueue q, WaveCounters *wcc, WaveCounters *wcs) -> int {
+      ShadowQueue sq{S.d_sq[0].as<float4>(), S.d_sq[1].as<float4>(), S.d_sq[2].as<float4>(), S.sq_cap};
+      cudaEvent_t e0 = get_event(S, ev_used), e1 = get_event(S, ev_used);
+      CU(cudaEventRecord(e0, st));
+      launch_trace(S.view, S.has_shapes, fp, primary, q, S.d_hits.as<float4>(), wcc, slot_lo, n_slots, sq, accum, wcs,
+                   S.grid_trace, st);
+      CU(cudaEventRecord(e1, st));
+      trace_spans.emplace_back(e0, e1);
+      ++launches;
+      return NRB_OK;
+    };
     for (uint32_t k = 0; k < fp.max_depth; ++k) {
-      int cur = (int)(k & 1u);
+      const int cur = (int)(k & 1u);
       uint64_t bound;
       if (k == 0) {
-        bound = n0;
+        bound = n_slots;  // hit records are indexed by slot in wave 0
       } else {
         if (k >= 2) {
           CU(cudaEventSynchronize(count_ev[k - 1]));
@@ -616,85 +632,93 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
         if (known_prev == 0 || S.child_factor == 0) break;
         bound = known_prev * (uint64_t)S.child_factor;
       }
-      // this wave's exact count arrives in pinned memory once the producer finished (k >= 1)
       if (wave_base + k >= S.h_wave_cap) return fail(NRB_ERR_INVALID_ARG, "max_depth too large for the wave-count buffer");
       if (k == 0) {
         S.h_wave_counts[wave_base] = (uint32_t)n0;
         count_ev.push_back(nullptr);
       } else {
-        CU(cudaMemcpyAsync(&S.h_wave_counts[wave_base + k], &dc->n_rays[cur], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&S.h_wave_counts[wave_base + k], &wc[k].n_rays, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         cudaEvent_t ev = get_event(S, ev_used);
         CU(cudaEventRecord(ev, st));
         count_ev.push_back(ev);
       }
       ++wave_counts_used;
-      uint64_t next_need = bound * (uint64_t)S.child_factor;
+      const uint64_t emitters = (k == 0) ? n0 : bound;  // rays that can spawn children / shadow rays
+      uint64_t next_need = emitters * (uint64_t)S.child_factor;
       if (next_need * 48 > mem_ceiling || next_need >= (1ull << 32))
         return fail(NRB_ERR_QUEUE_OVERFLOW, "secondary-ray queue would exceed NRB_QUEUE_BYTES");
       CU(ensure_ray_queue(S, 1 - cur, (uint32_t)next_need));
       if (bound > S.hits_cap) {
-        // growing a buffer frees the old one: drain the stream first (rare: first frames only)
-        CU(cudaStreamSynchronize(st));
+        CU(cudaStreamSynchronize(st));  // growing frees the old buffer: drain first (first frames only)
         CU(S.d_hits.ensure((size_t)bound * 16));
         S.hits_cap = (uint32_t)bound;
       }
-      uint32_t n_exact_or_bound = (uint32_t)bound;
-      uint32_t chunk = n_exact_or_bound;
+      uint32_t n_upper = (uint32_t)bound;
+      bool chunked = false;
+      uint32_t chunk = n_upper;
       if (S_total) {
-        uint64_t want = bound * S_total;
-        if (want > std::max<uint64_t>(shadow_cap_req, S_total)) {
-          // shadow rays of this wave may not fit: fall back to the exact count and chunk the wave
+        uint64_t want = emitters * S_total;
+        const uint64_t cap_limit = std::max<uint64_t>(shadow_cap_req, S_total);
+        if (want > cap_limit) {
+          // the shadow rays of this wave may not fit: use the exact count and chunk the wave
+          chunked = true;
           if (k >= 1) {
             CU(cudaEventSynchronize(count_ev[k]));
-            n_exact_or_bound = S.h_wave_counts[wave_base + k];
+            n_upper = S.h_wave_counts[wave_base + k];
           }
-          want = std::min<uint64_t>((uint64_t)n_exact_or_bound * S_total, std::max<uint64_t>(shadow_cap_req, S_total));
+          want = std::min<uint64_t>((uint64_t)n_upper * S_total, cap_limit);
         }
         if (want > S.sq_cap) {
+          // the queue may still hold the previous wave's untraced shadow rays: trace them before it moves
+          if (pending_shadow >= 0) {
+            rc = trace_span(false, no_queue, nullptr, &wc[pending_shadow]);
+            if (rc) return rc;
+            pending_shadow = -1;
+          }
           CU(cudaStreamSynchronize(st));
           for (int c = 0; c < 3; ++c) CU(S.d_sq[c].ensure((size_t)want * 16));
           S.sq_cap = (uint32_t)want;
         }
-        chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_exact_or_bound, S.sq_cap / S_total));
+        if (chunked) chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_upper, S.sq_cap / S_total));
       }
-      if (n_exact_or_bound == 0) break;
+      if (n_upper == 0) break;
       ShadowQueue sq{S.d_sq[0].as<float4>(), S.d_sq[1].as<float4>(), S.d_sq[2].as<float4>(), S.sq_cap};
-      CU(cudaMemsetAsync(&dc->n_rays[1 - cur], 0, sizeof(uint32_t), st));
-      CU(cudaMemsetAsync(&dc->fetch_closest, 0, sizeof(uint32_t), st));
-      // K2 closest hit
-      cudaEvent_t e0 = get_event(S, ev_used), e1 = get_event(S, ev_used);
-      CU(cudaEventRecord(e0, st));
-      launch_trace_closest(S.view, S.has_shapes, ray_queue(S, cur), S.d_hits.as<float4>(), &dc->n_rays[cur],
-                           &dc->fetch_closest, S.grid_closest, st);
-      CU(cudaEventRecord(e1, st));
-      closest_spans.emplace_back(e0, e1);
-      ++launches;
-      // K4 shade (+ K3 shadow) in chunks bounded by the shadow queue
-      for (uint32_t lo = 0; lo < n_exact_or_bound; lo += chunk) {
-        uint32_t hi = (uint32_t)std::min<uint64_t>(n_exact_or_bound, (uint64_t)lo + chunk);
-        if (S_total) CU(cudaMemsetAsync(&dc->n_shadow, 0, sizeof(uint32_t), st));
+      const RayQueue qin = (k == 0) ? no_queue : ray_queue(S, cur);
+      // trace: shadow rays left by the previous wave + closest hits of this wave
+      rc = trace_span(k == 0, qin, &wc[k], pending_shadow >= 0 ? &wc[pending_shadow] : nullptr);
+      if (rc) return rc;
+      pending_shadow = -1;
+      if (!chunked) {
         cudaEvent_t h0 = nullptr, h1 = nullptr;
         if (dump) {
           h0 = get_event(S, ev_used), h1 = get_event(S, ev_used);
           CU(cudaEventRecord(h0, st));
         }
-        launch_shade(S.view, S.has_shapes, fp, ray_queue(S, cur), S.d_hits.as<float4>(), &dc->n_rays[cur], lo, hi,
-                     ray_queue(S, 1 - cur), &dc->n_rays[1 - cur], sq, dc, accum, S.grid_shade, st);
+        launch_shade(S.view, S.has_shapes, fp, k == 0, qin, S.d_hits.as<float4>(), &wc[k], slot_lo, n_slots, 0, n_upper,
+                     ray_queue(S, 1 - cur), sq, dc, accum, S.grid_shade, st);
         if (dump) {
           CU(cudaEventRecord(h1, st));
           shade_spans.emplace_back(h0, h1);
         }
         ++launches;
-        if (S_total) {
-          CU(cudaMemsetAsync(&dc->fetch_shadow, 0, sizeof(uint32_t), st));
-          cudaEvent_t s0 = get_event(S, ev_used), s1 = get_event(S, ev_used);
-          CU(cudaEventRecord(s0, st));
-          launch_trace_shadow(S.view, S.has_shapes, sq, accum, &dc->n_shadow, &dc->fetch_shadow, S.grid_shadow, st);
-          CU(cudaEventRecord(s1, st));
-          shadow_spans.emplace_back(s0, s1);
+        if (S_total) pending_shadow = (int)k;
+      } else {
+        // rare path (area lights x huge waves): shade a slice, trace its shadow rays, repeat
+        for (uint32_t lo = 0; lo < n_upper; lo += chunk) {
+          uint32_t hi = (uint32_t)std::min<uint64_t>(n_upper, (uint64_t)lo + chunk);
+          launch_shade(S.view, S.has_shapes, fp, k == 0, qin, S.d_hits.as<float4>(), &wc[k], slot_lo, n_slots, lo, hi,
+                       ray_queue(S, 1 - cur), sq, dc, accum, S.grid_shade, st);
           ++launches;
+          rc = trace_span(false, no_queue, nullptr, &wc[k]);
+          if (rc) return rc;
+          CU(cudaMemsetAsync(&wc[k].n_shadow, 0, sizeof(uint32_t), st));
+          CU(cudaMemsetAsync(&wc[k].fetch_shadow, 0, sizeof(uint32_t), st));
         }
       }
+    }
+    if (pending_shadow >= 0) {
+      rc = trace_span(false, no_queue, nullptr, &wc[pending_shadow]);
+      if (rc) return rc;
     }
   }
   if (d_out8)
@@ -711,13 +735,13 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
     float total = 0.0f;
     cudaEventElapsedTime(&total, S.ev_begin, S.ev_end);
     fprintf(stderr, "[nrb] frame %.3f ms, %zu waves enqueued\n", total, wave_counts_used);
-    for (size_t i = 0; i < wave_counts_used; ++i) {
-      float tc = 0, th = 0, ts = 0, t0 = 0;
-      if (i < closest_spans.size()) cudaEventElapsedTime(&tc, closest_spans[i].first, closest_spans[i].second);
+    for (size_t i = 0; i < trace_spans.size(); ++i) {
+      float tt = 0, th = 0, t0 = 0;
+      cudaEventElapsedTime(&tt, trace_spans[i].first, trace_spans[i].second);
       if (i < shade_spans.size()) cudaEventElapsedTime(&th, shade_spans[i].first, shade_spans[i].second);
-      if (i < shadow_spans.size()) cudaEventElapsedTime(&ts, shadow_spans[i].first, shadow_spans[i].second);
-      if (i < closest_spans.size()) cudaEventElapsedTime(&t0, S.ev_begin, closest_spans[i].first);
-      fprintf(stderr, "[nrb]  wave %2zu n=%9u start=%.3f closest=%.3f shade=%.3f shadow=%.3f\n", i, S.h_wave_counts[i], t0, tc, th, ts);
+      cudaEventElapsedTime(&t0, S.ev_begin, trace_spans[i].first);
+      fprintf(stderr, "[nrb]  wave %2zu n=%9u start=%.3f trace=%.3f shade=%.3f\n", i,
+              i < wave_counts_used ? S.h_wave_counts[i] : 0u, t0, tt, th);
     }
   }
   if (S.h_counters->overflow) return fail(NRB_ERR_QUEUE_OVERFLOW, "a device queue overflowed (internal capacity bug)");
@@ -733,23 +757,16 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, S.ev_begin, S.ev_end);
     stats->ms_device = ms;
-    float tc = 0.0f, ts = 0.0f;
-    for (auto &sp : closest_spans) {
+    float tt = 0.0f;
+    for (auto &sp : trace_spans) {
       float t = 0.0f;
       cudaEventElapsedTime(&t, sp.first, sp.second);
-      tc += t;
+      tt += t;
     }
-    for (auto &sp : shadow_spans) {
-      float t = 0.0f;
-      cudaEventElapsedTime(&t, sp.first, sp.second);
-      ts += t;
-    }
-    stats->ms_closest = tc;
-    stats->ms_shadow = ts;
-    stats->launches_closest = (uint32_t)closest_spans.size();
-    stats->launches_shadow = (uint32_t)shadow_spans.size();
-    stats->ms_trace = tc + ts;
-    stats->ms_shade = ms - (tc + ts);
+    stats->ms_trace = tt;
+    stats->ms_shade = ms - tt;
+    stats->launches_trace = (uint32_t)trace_spans.size();
+    stats->launches_shade = launches - 1u - (uint32_t)trace_spans.size();
     stats->bvh_nodes = S.n_bvh_nodes;
     stats->triangles = S.n_tris;
     stats->scene_bytes = S.scene_bytes;
@@ -799,8 +816,7 @@ int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out) {
   CU(S->d_counters.ensure(sizeof(Counters)));
   int rc = build_scene(*desc, *S);
   if (rc) return rc;
-  S->grid_closest = S->sm_count * trace_blocks_per_sm(S->has_shapes, false);
-  S->grid_shadow = S->sm_count * trace_blocks_per_sm(S->has_shapes, true);
+  S->grid_trace = S->sm_count * trace_blocks_per_sm(S->has_shapes);
   S->grid_shade = S->sm_count * shade_blocks_per_sm(S->has_shapes);
   *out = S.release();
   return NRB_OK;

@@ -131,6 +131,7 @@ struct RayQueue {
 // Hit record, 16 bytes: (t, prim, u, v).  prim (uint bits): triangle index in leaf order, or
 // 0x80000000 | shape index, or kMiss.
 constexpr uint32_t kMiss = 0xFFFFFFFFu;
+constexpr uint32_t kSkip = 0xFFFFFFFEu;  // primary slot outside the image (ragged tile): no ray
 constexpr uint32_t kShapeBit = 0x80000000u;
 // Shadow ray record, 48 bytes in three columns:
 //   a = (o.xyz, tmax)   b = (d.xyz, pixel address as uint bits)   c = (contribution rgb, -)
@@ -139,14 +140,20 @@ struct ShadowQueue {
   uint32_t capacity;
 };
 
-// Device counters block (one per scene handle)
-struct Counters {
-  uint32_t n_rays[2];      // ray queue tails (ping-pong)
-  uint32_t n_shadow;       // shadow queue tail
-  uint32_t fetch_closest;  // persistent-kernel work counters
+// Per-wave queue counters: wave k reads its ray count from wc[k].n_rays (written by the shade of wave
+// k-1), its shade writes wc[k].n_shadow and wc[k+1].n_rays.  One zeroed array per batch: no counter
+// resets between kernels.
+struct WaveCounters {
+  uint32_t n_rays;         // rays in the queue this wave consumes
+  uint32_t n_shadow;       // shadow rays emitted by this wave's shade
+  uint32_t fetch_closest;  // persistent-kernel work cursors
   uint32_t fetch_shadow;
-  uint32_t overflow;       // set if any queue append was dropped
-  uint32_t _pad[2];
+};
+
+// Frame statistics block (one per scene handle)
+struct Counters {
+  uint32_t overflow;  // set if any queue append was dropped
+  uint32_t _pad[3];
   unsigned long long rays_reflect, rays_refract, rays_shadow, paths_truncated;
 };
 

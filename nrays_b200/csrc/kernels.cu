@@ -1,8 +1,8 @@
 // kernels.cu — the sm_100a kernels of the nrays render path (wavefront formulation).
 //
-//   K1 raygen_kernel          src/scene.rs:67-89      primary rays (jitter + unproject) -> ray queue
-//   K2 trace_closest_kernel   src/scene.rs:163-166, 262-283 + ncollide3d BVT/RayCast
-//   K3 trace_shadow_kernel    src/scene.rs:147-161, 285-339 (Scene::intersects_ray + transparent filter)
+//   K1 primary_ray()          src/scene.rs:67-89      jitter + unproject, fused into wave 0 of K2 and K4
+//   K2 trace_kernel/closest   src/scene.rs:163-166, 262-283 + ncollide3d BVT/RayCast
+//   K3 trace_kernel/shadow    src/scene.rs:147-161, 285-339 (Scene::intersects_ray + transparent filter)
 //   K4 shade_kernel           src/scene.rs:168-252, src/phong_material.rs:72-151, src/light.rs:56-63,
 //                             src/texture2d.rs:207-256, normal/uv materials
 //   K5 resolve_kernel         src/scene.rs:94 (tot_c / spp) [+ src/image.rs:64-77 RGB8 quantisation]
@@ -20,42 +20,6 @@ namespace nrb {
 // helpers
 // ---------------------------------------------------------------------------------------------
 NRB_DI uint32_t lane_id() { return threadIdx.x & 31u; }
-
-// Warp-aggregated queue append: one atomicAdd per warp, dense slots in lane order.
-NRB_DI uint32_t warp_append(uint32_t *tail, bool want) {
-  uint32_t mask = __ballot_sync(0xFFFFFFFFu, want);
-  if (mask == 0) return 0;
-  uint32_t leader = __ffs(mask) - 1;
-  uint32_t base = 0;
-  if (lane_id() == leader) base = atomicAdd(tail, __popc(mask));
-  base = __shfl_sync(0xFFFFFFFFu, base, leader);
-  return base + __popc(mask & ((1u << lane_id()) - 1u));
-}
-
-// Warp-aggregated append of a variable number of entries per lane (exclusive scan by shuffles);
-// the warp total is also added to `count_ctr` (ray statistics).
-NRB_DI uint32_t warp_append_n(uint32_t *tail, uint32_t n, unsigned long long *count_ctr) {
-  uint32_t incl = n;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if ((int)lane_id() >= o) incl += v;
-  }
-  uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-  uint32_t base = 0;
-  if (total == 0) return 0;
-  if (lane_id() == 0) {
-    base = atomicAdd(tail, total);
-    atomicAdd(count_ctr, (unsigned long long)total);
-  }
-  base = __shfl_sync(0xFFFFFFFFu, base, 0);
-  return base + incl - n;
-}
-
-NRB_DI void count_warp(unsigned long long *ctr, bool pred) {
-  uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
-  if (mask && lane_id() == (uint32_t)(__ffs(mask) - 1)) atomicAdd(ctr, (unsigned long long)__popc(mask));
-}
 
 // 8-bit Morton decode (4 bits x, 4 bits y) for the in-tile pixel order
 NRB_DI uint32_t compact4(uint32_t v) {
@@ -79,22 +43,23 @@ NRB_DI void accum_add(float4 *accum, uint32_t idx, V3 c) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1 — primary rays (src/scene.rs:67-89)
+// K1 — primary rays (src/scene.rs:67-89), generated on the fly.
+// Wave 0 never materialises its rays: the closest-hit kernel and the shade kernel both evaluate this
+// function for sample slot `slot` (identical arithmetic -> identical ray), so 48 B/ray of queue
+// writes and 80 B/ray of reads never touch HBM.  Slot order: tile-major, Morton inside the 16x16
+// tile, samples innermost, so a warp covers a compact pixel block.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) raygen_kernel(FrameParams fp, uint32_t slot_begin, uint32_t slot_end,
-                                                     RayQueue q, uint32_t *tail) {
-  uint32_t slot = slot_begin + blockIdx.x * blockDim.x + threadIdx.x;
-  bool valid = slot < slot_end;
+NRB_DI bool primary_ray(const FrameParams &fp, uint32_t slot, V3 &o, V3 &d, uint32_t &gid) {
   uint32_t per_tile = NRB_TILE * NRB_TILE * fp.spp;
   uint32_t lt = slot / per_tile, r = slot - lt * per_tile;
   uint32_t p = r / fp.spp, s = r - p * fp.spp;
   uint32_t tile = fp.tile_first + lt * fp.tile_stride;
   uint32_t ty = tile / fp.tiles_x, tx = tile - ty * fp.tiles_x;
   uint32_t x = tx * NRB_TILE + compact4(p), y = ty * NRB_TILE + compact4(p >> 1);
-  valid = valid && x < fp.width && y < fp.height;
+  if (x >= fp.width || y >= fp.height) return false;
   uint32_t ipt = y * fp.width + x;
   float jx = 0.0f, jy = 0.0f;
-  if (valid && fp.window != 0.0f) {
+  if (fp.window != 0.0f) {
     uint32_t rnd[4];
     philox4x32_10(ipt, s, 0u, 0u, fp.seed_lo, fp.seed_hi ^ kStreamPrimary, rnd);
     jx = (u24(rnd[0]) - 0.5f) * fp.window;
@@ -103,17 +68,14 @@ __global__ void __launch_bounds__(256) raygen_kernel(FrameParams fp, uint32_t sl
   float fx = (float)x + jx, fy = (float)y + jy;
   float ndx = (fx * fp.inv_w - 0.5f) * 2.0f;
   float ndy = -(fy * fp.inv_h - 0.5f) * 2.0f;
-  V3 d = mk(fp.dx[0], fp.dx[1], fp.dx[2]) * ndx + mk(fp.dy[0], fp.dy[1], fp.dy[2]) * ndy + mk(fp.d0[0], fp.d0[1], fp.d0[2]);
+  V3 dir = mk(fp.dx[0], fp.dx[1], fp.dx[2]) * ndx + mk(fp.dy[0], fp.dy[1], fp.dy[2]) * ndy + mk(fp.d0[0], fp.d0[1], fp.d0[2]);
   float w = fp.wx * ndx + fp.wy * ndy + fp.w0;
-  d = normalize(d);
-  if (w < 0.0f) d = -d;
-  uint32_t idx = warp_append(tail, valid);
-  if (valid && idx < q.capacity) {
-    q.a[idx] = make_float4(fp.eye[0], fp.eye[1], fp.eye[2], d.x);
-    q.b[idx] = make_float4(d.y, d.z, 1.0f /*weight*/, 1.0f /*energy*/);
-    q.c[idx] = make_float4(1.0f /*refr*/, __uint_as_float(ipt * fp.spp + s), __uint_as_float(1u) /*path*/,
-                           __uint_as_float(0u) /*depth*/);
-  }
+  dir = normalize(dir);
+  if (w < 0.0f) dir = -dir;
+  o = mk(fp.eye[0], fp.eye[1], fp.eye[2]);
+  d = dir;
+  gid = ipt * fp.spp + s;
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -204,38 +166,24 @@ NRB_DI bool traverse(const SceneView &sc, int root, V3 o, V3 d, float tmax, Hit 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2 — closest hit (Scene::trace's best_first_search, src/scene.rs:164-166)
-// Persistent warps: each warp pulls packets of 32 rays from the queue with one atomic.
+// K2 — closest hit of one ray (Scene::trace's best_first_search, src/scene.rs:164-166)
 // ---------------------------------------------------------------------------------------------
 template <bool HAS_SHAPES>
-__global__ void __launch_bounds__(kTraceBlock) trace_closest_kernel(SceneView sc, RayQueue q, float4 *hits,
-                                                                   const uint32_t *count_ptr, uint32_t *fetch) {
-  const uint32_t count = *count_ptr;
-  while (true) {
-    uint32_t base = 0;
-    if (lane_id() == 0) base = atomicAdd(fetch, 32u);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= count) break;
-    uint32_t i = base + lane_id();
-    if (i < count) {
-      float4 a = q.a[i], b = q.b[i];
-      V3 o = mk(a.x, a.y, a.z), d = mk(a.w, b.x, b.y);
-      Hit hit;
-      hit.t = 3.402823466e+38f, hit.prim = kMiss, hit.u = hit.v = 0.0f;
-      if (HAS_SHAPES) {
-        // planes have infinite AABBs: always tested, never in the BVH
-        for (int p = 0; p < sc.n_planes; ++p) {
-          int si = sc.planes[p];
-          Inter it;
-          if (cast_shape(sc.shapes[si], o, d, it) && it.toi < hit.t) {
-            hit.t = it.toi, hit.prim = kShapeBit | (uint32_t)si, hit.u = 0.0f, hit.v = 0.0f;
-          }
-        }
+NRB_DI float4 closest_hit(const SceneView &sc, V3 o, V3 d) {
+  Hit hit;
+  hit.t = 3.402823466e+38f, hit.prim = kMiss, hit.u = hit.v = 0.0f;
+  if (HAS_SHAPES) {
+    // planes have infinite AABBs: always tested, never in the BVH
+    for (int p = 0; p < sc.n_planes; ++p) {
+      int si = sc.planes[p];
+      Inter it;
+      if (cast_shape(sc.shapes[si], o, d, it) && it.toi < hit.t) {
+        hit.t = it.toi, hit.prim = kShapeBit | (uint32_t)si, hit.u = 0.0f, hit.v = 0.0f;
       }
-      if (sc.root_all != kEmpty) traverse<HAS_SHAPES, false>(sc, sc.root_all, o, d, hit.t, hit);
-      hits[i] = make_float4(hit.t, __uint_as_float(hit.prim), hit.u, hit.v);
     }
   }
+  if (sc.root_all != kEmpty) traverse<HAS_SHAPES, false>(sc, sc.root_all, o, d, hit.t, hit);
+  return make_float4(hit.t, __uint_as_float(hit.prim), hit.u, hit.v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -317,78 +265,143 @@ NRB_DI bool shadow_candidate(const SceneView &sc, int root, int node_id, V3 o, V
 }
 
 template <bool HAS_SHAPES>
-__global__ void __launch_bounds__(kTraceBlock) trace_shadow_kernel(SceneView sc, ShadowQueue q, float4 *accum,
-                                                                  const uint32_t *count_ptr, uint32_t *fetch) {
-  const uint32_t count = min(*count_ptr, q.capacity);
-  while (true) {
-    uint32_t base = 0;
-    if (lane_id() == 0) base = atomicAdd(fetch, 32u);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= count) break;
-    uint32_t i = base + lane_id();
-    if (i < count) {
-      float4 a = q.a[i], b = q.b[i];
-      V3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
-      float tmax = a.w;
-      bool occluded = false;
-      V3 filter = mk(1, 1, 1);
-      if (HAS_SHAPES) {
-        for (int p = 0; p < sc.n_planes && !occluded; ++p) {
-          int si = sc.planes[p];
-          const Shape &sh = sc.shapes[si];
-          if (sc.node_info[sh.node].flags & 1) {
-            // transparent candidate plane: its (only) hit filters or occludes
-            Inter it;
-            if (cast_shape(sh, o, d, it) && it.toi <= tmax) {
-              Surface s;
-              s.n = it.n, s.u = it.u, s.v = it.v, s.has_uv = it.has_uv, s.node = sh.node;
-              const NodeInfo ni = sc.node_info[sh.node];
-              float4 c = mat_ambiant(sc, sc.materials[ni.material], s);
-              float alpha = c.w * ni.alpha;
-              if (alpha < 1.0f) {
-                float k = 1.0f - alpha;
-                filter = mk(filter.x * c.x * k, filter.y * c.y * k, filter.z * c.z * k);
-              } else {
-                occluded = true;
-              }
-            }
+NRB_DI void shadow_ray(const SceneView &sc, const ShadowQueue &q, uint32_t i, float4 *accum) {
+  float4 a = q.a[i], b = q.b[i];
+  V3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
+  float tmax = a.w;
+  bool occluded = false;
+  V3 filter = mk(1, 1, 1);
+  if (HAS_SHAPES) {
+    for (int p = 0; p < sc.n_planes && !occluded; ++p) {
+      int si = sc.planes[p];
+      const Shape &sh = sc.shapes[si];
+      if (sc.node_info[sh.node].flags & 1) {
+        // transparent candidate plane: its (only) hit filters or occludes
+        Inter it;
+        if (cast_shape(sh, o, d, it) && it.toi <= tmax) {
+          Surface s;
+          s.n = it.n, s.u = it.u, s.v = it.v, s.has_uv = it.has_uv, s.node = sh.node;
+          const NodeInfo ni = sc.node_info[sh.node];
+          float4 c = mat_ambiant(sc, sc.materials[ni.material], s);
+          float alpha = c.w * ni.alpha;
+          if (alpha < 1.0f) {
+            float k = 1.0f - alpha;
+            filter = mk(filter.x * c.x * k, filter.y * c.y * k, filter.z * c.z * k);
           } else {
-            Inter it;
-            if (cast_shape(sh, o, d, it) && it.toi <= tmax) occluded = true;
+            occluded = true;
           }
         }
-      }
-      if (!occluded && sc.root_opaque != kEmpty) {
-        Hit h;
-        occluded = traverse<HAS_SHAPES, true>(sc, sc.root_opaque, o, d, tmax, h);
-      }
-      if (!occluded) {
-        for (int c = 0; c < sc.n_candidates && !occluded; ++c) {
-          const Candidate cd = sc.candidates[c];
-          // slab test against the candidate's box (bv cost), origin-inside counts as hit
-          float t0 = 0.0f, t1 = tmax;
-          bool miss = false;
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax) {
-            float oi = comp(o, ax), di = comp(d, ax);
-            if (di == 0.0f) {
-              if (oi < cd.lo[ax] || oi > cd.hi[ax]) miss = true;
-            } else {
-              float inv = 1.0f / di;
-              float ta = (cd.lo[ax] - oi) * inv, tb = (cd.hi[ax] - oi) * inv;
-              t0 = fmaxf(t0, fminf(ta, tb));
-              t1 = fminf(t1, fmaxf(ta, tb));
-            }
-          }
-          if (miss || t0 > t1) continue;
-          occluded = shadow_candidate<HAS_SHAPES>(sc, cd.root, cd.node, o, d, tmax, filter);
-        }
-      }
-      if (!occluded) {
-        float4 cc = q.c[i];
-        accum_add(accum, __float_as_uint(b.w), mk(cc.x * filter.x, cc.y * filter.y, cc.z * filter.z));
+      } else {
+        Inter it;
+        if (cast_shape(sh, o, d, it) && it.toi <= tmax) occluded = true;
       }
     }
+  }
+  if (!occluded && sc.root_opaque != kEmpty) {
+    Hit h;
+    occluded = traverse<HAS_SHAPES, true>(sc, sc.root_opaque, o, d, tmax, h);
+  }
+  if (!occluded) {
+    for (int c = 0; c < sc.n_candidates && !occluded; ++c) {
+      const Candidate cd = sc.candidates[c];
+      // slab test against the candidate's box (bv cost), origin-inside counts as hit
+      float t0 = 0.0f, t1 = tmax;
+      bool miss = false;
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        float oi = comp(o, ax), di = comp(d, ax);
+        if (di == 0.0f) {
+          if (oi < cd.lo[ax] || oi > cd.hi[ax]) miss = true;
+        } else {
+          float inv = 1.0f / di;
+          float ta = (cd.lo[ax] - oi) * inv, tb = (cd.hi[ax] - oi) * inv;
+          t0 = fmaxf(t0, fminf(ta, tb));
+          t1 = fminf(t1, fmaxf(ta, tb));
+        }
+      }
+      if (miss || t0 > t1) continue;
+      occluded = shadow_candidate<HAS_SHAPES>(sc, cd.root, cd.node, o, d, tmax, filter);
+    }
+  }
+  if (!occluded) {
+    float4 cc = q.c[i];
+    accum_add(accum, __float_as_uint(b.w), mk(cc.x * filter.x, cc.y * filter.y, cc.z * filter.z));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The persistent trace kernel: ONE launch per wave drains the shadow queue of the previous wave
+// (any-hit + transparent filter, adds into the pixel accumulator) and then the ray queue of this
+// wave (closest hit -> hit records).  Grid = SMs x resident CTAs; each warp pulls packets of
+// kFetchPackets x 32 rays with one atomic on a per-wave cursor.  PRIMARY: wave 0 generates its rays
+// from the sample slot instead of reading a queue.
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_SHAPES>
+NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *accum, WaveCounters *wc_shadow) {
+  const uint32_t lane = lane_id();
+  const uint32_t count = min(wc_shadow->n_shadow, sq.capacity);
+  while (true) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&wc_shadow->fetch_shadow, 32u * kFetchPackets);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= count) break;
+#pragma unroll 1
+    for (int pk = 0; pk < kFetchPackets; ++pk) {
+      uint32_t i = base + 32u * pk + lane;
+      if (i < count) shadow_ray<HAS_SHAPES>(sc, sq, i, accum);
+    }
+  }
+}
+
+template <bool HAS_SHAPES, bool PRIMARY>
+NRB_DI void drain_closest(const SceneView &sc, const FrameParams &fp, const RayQueue &q, float4 *hits,
+                          WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots) {
+  const uint32_t lane = lane_id();
+  const uint32_t count = PRIMARY ? n_slots : wc_closest->n_rays;
+  while (true) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&wc_closest->fetch_closest, 32u * kFetchPackets);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= count) break;
+#pragma unroll 1
+    for (int pk = 0; pk < kFetchPackets; ++pk) {
+      uint32_t i = base + 32u * pk + lane;
+      if (i < count) {
+        V3 o, d;
+        bool valid = true;
+        if (PRIMARY) {
+          uint32_t gid;
+          valid = primary_ray(fp, slot_lo + i, o, d, gid);
+        } else {
+          float4 a = q.a[i], b = q.b[i];
+          o = mk(a.x, a.y, a.z), d = mk(a.w, b.x, b.y);
+        }
+        // slots outside the image (ragged tiles) are marked so shade skips them
+        hits[i] = valid ? closest_hit<HAS_SHAPES>(sc, o, d) : make_float4(0.0f, __uint_as_float(kSkip), 0.0f, 0.0f);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The persistent trace kernel: ONE launch per wave drains the shadow queue of the previous wave
+// (any-hit + transparent filter, adds into the pixel accumulator) and the ray queue of this wave
+// (closest hit -> hit records).  Grid = SMs x resident CTAs; each warp pulls packets of
+// kFetchPackets x 32 rays with one atomic on a per-wave cursor.  Even CTAs start on the shadow queue,
+// odd CTAs on the ray queue, then swap: in small (latency-bound) waves both queues progress at once.
+// PRIMARY: wave 0 generates its rays from the sample slot instead of reading a queue.
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_SHAPES, bool PRIMARY>
+__global__ void __launch_bounds__(kTraceBlock) trace_kernel(SceneView sc, FrameParams fp, RayQueue q, float4 *hits,
+                                                           WaveCounters *wc_closest, uint32_t slot_lo,
+                                                           uint32_t n_slots, ShadowQueue sq, float4 *accum,
+                                                           WaveCounters *wc_shadow) {
+  if (blockIdx.x & 1u) {
+    if (wc_closest) drain_closest<HAS_SHAPES, PRIMARY>(sc, fp, q, hits, wc_closest, slot_lo, n_slots);
+    if (wc_shadow) drain_shadow<HAS_SHAPES>(sc, sq, accum, wc_shadow);
+  } else {
+    if (wc_shadow) drain_shadow<HAS_SHAPES>(sc, sq, accum, wc_shadow);
+    if (wc_closest) drain_closest<HAS_SHAPES, PRIMARY>(sc, fp, q, hits, wc_closest, slot_lo, n_slots);
   }
 }
 
@@ -404,17 +417,19 @@ struct ShadeShared {
   uint32_t base[2];  // their first slots in the global queues
 };
 
-template <bool HAS_SHAPES>
+template <bool HAS_SHAPES, bool PRIMARY>
 __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(SceneView sc, FrameParams fp, RayQueue qin,
-                                                                            const float4 *hits,
-                                                                            const uint32_t *count_ptr, uint32_t lo,
-                                                                            uint32_t hi, RayQueue qout,
-                                                                            uint32_t *tail_out, ShadowQueue sq,
-                                                                            Counters *ctr, float4 *accum) {
+                                                                            const float4 *hits, WaveCounters *wc,
+                                                                            uint32_t slot_lo, uint32_t n_slots,
+                                                                            uint32_t lo, uint32_t hi, RayQueue qout,
+                                                                            ShadowQueue sq, Counters *ctr,
+                                                                            float4 *accum) {
+  uint32_t *const tail_out = &wc[1].n_rays;   // next wave's ray count
+  uint32_t *const tail_shadow = &wc[0].n_shadow;
   __shared__ ShadeShared sm;
   if (threadIdx.x < 2) sm.cnt[threadIdx.x] = 0;
   __syncthreads();
-  const uint32_t end = min(hi, *count_ptr);
+  const uint32_t end = min(hi, PRIMARY ? n_slots : wc[0].n_rays);
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t lane = lane_id();
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -422,16 +437,23 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
 
   for (uint32_t bb = lo + blockIdx.x * blockDim.x; bb < end; bb += stride) {  // block-uniform trip count
     const uint32_t i = bb + threadIdx.x;
-    const bool active = i < end;
-    float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra, h = ra;
-    if (active) {
-      ra = qin.a[i], rb = qin.b[i], rc = qin.c[i];
-      h = hits[i];
-    }
-    V3 o = mk(ra.x, ra.y, ra.z), d = mk(ra.w, rb.x, rb.y);
-    float weight = rb.z, energy = rb.w, refr = rc.x;
-    uint32_t gid = __float_as_uint(rc.y), path = __float_as_uint(rc.z), depth = __float_as_uint(rc.w);
+    bool active = i < end;
+    float4 h = make_float4(0, 0, 0, 0);
+    if (active) h = hits[i];
     uint32_t prim = __float_as_uint(h.y);
+    V3 o = mk(0, 0, 0), d = mk(0, 0, 1);
+    float weight = 1.0f, energy = 1.0f, refr = 1.0f;
+    uint32_t gid = 0u, path = 1u, depth = 0u;
+    if (PRIMARY) {
+      // RayWithEnergy::new: refr 1.0, energy 1.0 (src/ray_with_energy.rs:11-13); ray regenerated from the slot
+      active = active && prim != kSkip;
+      if (active) primary_ray(fp, slot_lo + i, o, d, gid);
+    } else if (active) {
+      float4 ra = qin.a[i], rb = qin.b[i], rc = qin.c[i];
+      o = mk(ra.x, ra.y, ra.z), d = mk(ra.w, rb.x, rb.y);
+      weight = rb.z, energy = rb.w, refr = rc.x;
+      gid = __float_as_uint(rc.y), path = __float_as_uint(rc.z), depth = __float_as_uint(rc.w);
+    }
     uint32_t ipt = gid / fp.spp, smp = gid - ipt * fp.spp;
     uint32_t pix = active ? accum_index(fp, ipt) : 0u;
 
@@ -505,7 +527,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
     __syncthreads();
     if (threadIdx.x == 0) {
       uint32_t t = sm.cnt[0];
-      sm.base[0] = t ? atomicAdd(&ctr->n_shadow, t) : 0u;
+      sm.base[0] = t ? atomicAdd(tail_shadow, t) : 0u;
       sm.cnt[0] = 0;
     } else if (threadIdx.x == 32) {
       uint32_t t = sm.cnt[1];
@@ -647,45 +669,50 @@ __global__ void untile_kernel(const float *gathered, uint32_t n_ranks, uint32_t 
 // ---------------------------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------------------------
-void launch_raygen(const FrameParams &fp, uint32_t slot_begin, uint32_t slot_end, RayQueue q, uint32_t *tail,
-                   cudaStream_t st) {
-  uint32_t n = slot_end - slot_begin;
-  if (!n) return;
-  raygen_kernel<<<(n + 255) / 256, 256, 0, st>>>(fp, slot_begin, slot_end, q, tail);
+void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue q, float4 *hits,
+                  WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, ShadowQueue sq, float4 *accum,
+                  WaveCounters *wc_shadow, int grid, cudaStream_t st) {
+  if (!wc_closest && !wc_shadow) return;
+  if (has_shapes) {
+    if (primary)
+      trace_kernel<true, true><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow);
+    else
+      trace_kernel<true, false><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow);
+  } else {
+    if (primary)
+      trace_kernel<false, true><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow);
+    else
+      trace_kernel<false, false><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow);
+  }
 }
 
-void launch_trace_closest(const SceneView &sc, bool has_shapes, RayQueue q, float4 *hits, const uint32_t *count,
-                          uint32_t *fetch, int grid, cudaStream_t st) {
-  if (has_shapes)
-    trace_closest_kernel<true><<<grid, kTraceBlock, 0, st>>>(sc, q, hits, count, fetch);
-  else
-    trace_closest_kernel<false><<<grid, kTraceBlock, 0, st>>>(sc, q, hits, count, fetch);
-}
-
-void launch_trace_shadow(const SceneView &sc, bool has_shapes, ShadowQueue q, float4 *accum, const uint32_t *count,
-                         uint32_t *fetch, int grid, cudaStream_t st) {
-  if (has_shapes)
-    trace_shadow_kernel<true><<<grid, kTraceBlock, 0, st>>>(sc, q, accum, count, fetch);
-  else
-    trace_shadow_kernel<false><<<grid, kTraceBlock, 0, st>>>(sc, q, accum, count, fetch);
-}
-
-void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, RayQueue qin, const float4 *hits,
-                  const uint32_t *count, uint32_t lo, uint32_t hi, RayQueue qout, uint32_t *tail_out, ShadowQueue sq,
-                  Counters *ctr, float4 *accum, int grid, cudaStream_t st) {
+void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue qin,
+                  const float4 *hits, WaveCounters *wc, uint32_t slot_lo, uint32_t n_slots, uint32_t lo, uint32_t hi,
+                  RayQueue qout, ShadowQueue sq, Counters *ctr, float4 *accum, int grid, cudaStream_t st) {
   if (hi <= lo) return;
-  if (has_shapes)
-    shade_kernel<true><<<grid, kShadeBlock, 0, st>>>(sc, fp, qin, hits, count, lo, hi, qout, tail_out, sq, ctr, accum);
-  else
-    shade_kernel<false><<<grid, kShadeBlock, 0, st>>>(sc, fp, qin, hits, count, lo, hi, qout, tail_out, sq, ctr, accum);
+  if (has_shapes) {
+    if (primary)
+      shade_kernel<true, true><<<grid, kShadeBlock, 0, st>>>(sc, fp, qin, hits, wc, slot_lo, n_slots, lo, hi, qout, sq, ctr, accum);
+    else
+      shade_kernel<true, false><<<grid, kShadeBlock, 0, st>>>(sc, fp, qin, hits, wc, slot_lo, n_slots, lo, hi, qout, sq, ctr, accum);
+  } else {
+    if (primary)
+      shade_kernel<false, true><<<grid, kShadeBlock, 0, st>>>(sc, fp, qin, hits, wc, slot_lo, n_slots, lo, hi, qout, sq, ctr, accum);
+    else
+      shade_kernel<false, false><<<grid, kShadeBlock, 0, st>>>(sc, fp, qin, hits, wc, slot_lo, n_slots, lo, hi, qout, sq, ctr, accum);
+  }
 }
 
 int shade_blocks_per_sm(bool has_shapes) {
-  int nb = 0;
-  if (has_shapes)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, shade_kernel<true>, kShadeBlock, 0);
-  else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, shade_kernel<false>, kShadeBlock, 0);
+  int nb = 0, nb2 = 0;
+  if (has_shapes) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, shade_kernel<true, false>, kShadeBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, shade_kernel<true, true>, kShadeBlock, 0);
+  } else {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, shade_kernel<false, false>, kShadeBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, shade_kernel<false, true>, kShadeBlock, 0);
+  }
+  nb = nb < nb2 ? nb : nb2;
   return nb > 0 ? nb : 1;
 }
 
@@ -706,19 +733,16 @@ void launch_untile(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_r
   untile_kernel<<<(n + 255) / 256, 256, 0, st>>>(gathered, n_ranks, tiles_per_rank, width, height, tiles_x, out_rgb);
 }
 
-int trace_blocks_per_sm(bool has_shapes, bool shadow) {
-  int nb = 0;
-  if (shadow) {
-    if (has_shapes)
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_shadow_kernel<true>, kTraceBlock, 0);
-    else
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_shadow_kernel<false>, kTraceBlock, 0);
+int trace_blocks_per_sm(bool has_shapes) {
+  int nb = 0, nb2 = 0;
+  if (has_shapes) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<true, false>, kTraceBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, trace_kernel<true, true>, kTraceBlock, 0);
   } else {
-    if (has_shapes)
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_closest_kernel<true>, kTraceBlock, 0);
-    else
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_closest_kernel<false>, kTraceBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<false, false>, kTraceBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, trace_kernel<false, true>, kTraceBlock, 0);
   }
+  nb = nb < nb2 ? nb : nb2;
   return nb > 0 ? nb : 1;
 }
 

@@ -5,23 +5,21 @@
 namespace nrb {
 
 constexpr int kTraceBlock = 128;
+constexpr int kFetchPackets = 2;  // 32-ray packets a warp takes per cursor atomic
 constexpr int kShadeBlock = 128;
 constexpr int kShadeMinBlocks = 6;  // caps shade at 80 registers -> 768 resident threads / SM (8 spills too much)
 
-void launch_raygen(const FrameParams &fp, uint32_t slot_begin, uint32_t slot_end, RayQueue q, uint32_t *tail,
-                   cudaStream_t st);
-void launch_trace_closest(const SceneView &sc, bool has_shapes, RayQueue q, float4 *hits, const uint32_t *count,
-                          uint32_t *fetch, int grid, cudaStream_t st);
-void launch_trace_shadow(const SceneView &sc, bool has_shapes, ShadowQueue q, float4 *accum, const uint32_t *count,
-                         uint32_t *fetch, int grid, cudaStream_t st);
-void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, RayQueue qin, const float4 *hits,
-                  const uint32_t *count, uint32_t lo, uint32_t hi, RayQueue qout, uint32_t *tail_out, ShadowQueue sq,
-                  Counters *ctr, float4 *accum, int grid, cudaStream_t st);
+void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue q, float4 *hits,
+                  WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, ShadowQueue sq, float4 *accum,
+                  WaveCounters *wc_shadow, int grid, cudaStream_t st);
+void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue qin,
+                  const float4 *hits, WaveCounters *wc, uint32_t slot_lo, uint32_t n_slots, uint32_t lo, uint32_t hi,
+                  RayQueue qout, ShadowQueue sq, Counters *ctr, float4 *accum, int grid, cudaStream_t st);
 int shade_blocks_per_sm(bool has_shapes);
 void launch_resolve(const float4 *accum, uint32_t n, uint32_t spp, float *out_rgb, cudaStream_t st);
 void launch_resolve_rgb8(const float4 *accum, uint32_t n, uint32_t spp, uint8_t *out, cudaStream_t st);
 void launch_untile(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width, uint32_t height,
                    float *out_rgb, cudaStream_t st);
-int trace_blocks_per_sm(bool has_shapes, bool shadow);
+int trace_blocks_per_sm(bool has_shapes);
 
 }  // namespace nrb

@@ -27,6 +27,6 @@ for f in range(frames):
     _lib.check(lib.nrb_render_device(scene.handle, C.byref(cam), C.c_void_p(out.data_ptr()), C.byref(st)))
     wall = (time.perf_counter() - t0) * 1e3
     d = st.as_dict()
-    print("frame %d wall %.3f ms device %.3f closest %.3f shadow %.3f other %.3f rays %d -> %.0f Mrays/s launches %d waves %d" % (
-        f, wall, d["ms_device"], d["ms_closest"], d["ms_shadow"], d["ms_shade"], d["rays_total"], d["rays_total"] / d["ms_device"] / 1e3,
+    print("frame %d wall %.3f ms device %.3f trace %.3f other %.3f rays %d -> %.0f Mrays/s launches %d waves %d" % (
+        f, wall, d["ms_device"], d["ms_trace"], d["ms_shade"], d["rays_total"], d["rays_total"] / d["ms_device"] / 1e3,
         d["kernel_launches"], d["waves"]))
