@@ -8,7 +8,7 @@ import os
 from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libnrays_b200.so")
+LIB_PATH = os.environ.get("NRB_LIB") or os.path.join(_HERE, "csrc", "libnrays_b200.so")  # NRB_LIB: kernel-variant experiments
 _lib = None
 
 

@@ -83,7 +83,7 @@ struct NrbScene {
   bool has_shapes = false;
   int child_factor = 0;  // max secondary rays per ray (reflection + refraction possible in this scene)
   uint64_t n_bvh_nodes = 0, n_tris = 0, scene_bytes = 0;
-  int grid_trace = 148;
+  int grid_trace = 148, grid_tail = 148;
   // frame state
   DevBuf d_q[2][3], d_hits, d_sq[3], d_accum, d_counters, d_wave, d_out, d_out8;
   uint32_t q_cap[2] = {0, 0}, sq_cap = 0, hits_cap = 0;
@@ -578,6 +578,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   const uint64_t shadow_cap_req = env_size("NRB_SHADOW_CAP", 16u << 20);
   const uint64_t mem_ceiling = env_size("NRB_QUEUE_BYTES", 64ull << 30);
   const uint32_t S_total = (uint32_t)S.view.shadow_samples;
+  const uint64_t tail_threshold = env_size("NRB_TAIL_RAYS", 1u << 20);
   uint64_t primary = 0;
 
   const size_t wc_len = (size_t)fp.max_depth + 3;
@@ -631,6 +632,44 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
         }
         if (known_prev == 0 || S.child_factor == 0) break;
         bound = known_prev * (uint64_t)S.child_factor;
+        if (k >= 2 && bound <= tail_threshold) {
+          // ---- tail: every lane follows its own ray chain to the end (see tail_kernel) -----------
+          if (pending_shadow >= 0) {
+            rc = trace_span(false, no_queue, nullptr, &wc[pending_shadow]);
+            if (rc) return rc;
+            pending_shadow = -1;
+          }
+          for (uint32_t t = k; t < fp.max_depth; ++t) {
+            const int tc = (int)(t & 1u);
+            if (wave_base + t + 1 >= S.h_wave_cap) return fail(NRB_ERR_INVALID_ARG, "max_depth too large for the wave-count buffer");
+            CU(ensure_ray_queue(S, 1 - tc, (uint32_t)std::max<uint64_t>(bound * 4, 4096)));  // spill queue
+            if (S_total && S.sq_cap < 65536) {
+              CU(cudaStreamSynchronize(st));
+              for (int c = 0; c < 3; ++c) CU(S.d_sq[c].ensure((size_t)65536 * 16));
+              S.sq_cap = 65536;
+            }
+            ShadowQueue sq{S.d_sq[0].as<float4>(), S.d_sq[1].as<float4>(), S.d_sq[2].as<float4>(), S.sq_cap};
+            cudaEvent_t e0 = get_event(S, ev_used), e1 = get_event(S, ev_used);
+            CU(cudaEventRecord(e0, st));
+            launch_tail(S.view, S.has_shapes, fp, ray_queue(S, tc), &wc[t], ray_queue(S, 1 - tc), sq, dc, accum, S.grid_tail, st);
+            CU(cudaEventRecord(e1, st));
+            trace_spans.emplace_back(e0, e1);
+            ++launches;
+            if (S_total) {
+              rc = trace_span(false, no_queue, nullptr, &wc[t]);  // the chains' shadow rays
+              if (rc) return rc;
+            }
+            // rays spilled by hits that spawned both children start the next tail launch
+            CU(cudaMemcpyAsync(&S.h_wave_counts[wave_base + t], &wc[t].n_rays, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(&S.h_wave_counts[wave_base + t + 1], &wc[t + 1].n_rays, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            wave_counts_used = std::max(wave_counts_used, wave_base + t + 1);
+            uint32_t spilled = S.h_wave_counts[wave_base + t + 1];
+            if (spilled == 0 || S.child_factor < 2) break;
+            bound = spilled;
+          }
+          break;
+        }
       }
       if (wave_base + k >= S.h_wave_cap) return fail(NRB_ERR_INVALID_ARG, "max_depth too large for the wave-count buffer");
       if (k == 0) {
@@ -735,6 +774,11 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
     float total = 0.0f;
     cudaEventElapsedTime(&total, S.ev_begin, S.ev_end);
     fprintf(stderr, "[nrb] frame %.3f ms, %zu waves enqueued\n", total, wave_counts_used);
+    unsigned long long dbg[4];
+    debug_visit_counters(dbg, true);
+    if (dbg[2])
+      fprintf(stderr, "[nrb] traversals %llu: %.1f node visits, %.1f triangle tests each, longest %llu steps (since last dump)\n",
+              dbg[2], (double)dbg[0] / dbg[2], (double)dbg[1] / dbg[2], dbg[3]);
     for (size_t i = 0; i < trace_spans.size(); ++i) {
       float tt = 0, th = 0, t0 = 0;
       cudaEventElapsedTime(&tt, trace_spans[i].first, trace_spans[i].second);
@@ -817,6 +861,7 @@ int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out) {
   int rc = build_scene(*desc, *S);
   if (rc) return rc;
   S->grid_trace = S->sm_count * trace_blocks_per_sm(S->has_shapes);
+  S->grid_tail = S->sm_count * 4;
   S->grid_shade = S->sm_count * shade_blocks_per_sm(S->has_shapes);
   *out = S.release();
   return NRB_OK;

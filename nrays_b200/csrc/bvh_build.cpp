@@ -3,13 +3,15 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace nrb {
 
 namespace {
 constexpr int kBins = 16;
-constexpr float kCostNode = 1.2f;  // relative cost of one two-box node visit vs one triangle test
+float kCostNode = 1.2f;  // relative cost of one two-box node visit vs one triangle test (env NRB_BVH_CNODE)
+int kLeafMax = kMaxLeafTris;  // env NRB_BVH_LEAF (<= kMaxLeafTris)
 constexpr int kForceMedianDepth = 36;
 
 inline float centroid(const Box &b, int axis) { return 0.5f * (b.lo[axis] + b.hi[axis]); }
@@ -37,6 +39,8 @@ void pad_box(Box &b, float scene_extent) {
 }
 
 int BvhBuilder::build_triangles(std::vector<BuildItem> &items, Box *root_box) {
+  if (const char *e = getenv("NRB_BVH_CNODE")) kCostNode = (float)atof(e);
+  if (const char *e = getenv("NRB_BVH_LEAF")) kLeafMax = std::max(1, std::min(kMaxLeafTris, atoi(e)));
   return build_rec(items.data(), items.size(), false, 0, root_box);
 }
 
@@ -63,7 +67,7 @@ int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, B
     return make_leaf(first, (uint32_t)n, false);
   };
 
-  size_t max_leaf = payload ? 1 : (size_t)kMaxLeafTris;
+  size_t max_leaf = payload ? 1 : (size_t)kLeafMax;
   if (n == 1) return make_leaf_node();
 
   // ---- choose a split ---------------------------------------------------------------------

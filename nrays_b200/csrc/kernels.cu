@@ -81,6 +81,10 @@ NRB_DI bool primary_ray(const FrameParams &fp, uint32_t slot, V3 &o, V3 &d, uint
 // ---------------------------------------------------------------------------------------------
 // BVH traversal (per-lane while-while with an explicit stack)
 // ---------------------------------------------------------------------------------------------
+#ifdef NRB_COUNT_VISITS
+__device__ unsigned long long g_dbg[4];  // nodes, tris, rays, -
+#endif
+
 struct Hit {
   float t;
   uint32_t prim;
@@ -102,10 +106,16 @@ NRB_DI bool traverse(const SceneView &sc, int root, V3 o, V3 d, float tmax, Hit 
   float idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
   float oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;
   float tbest = tmax;
+#ifdef NRB_COUNT_VISITS
+  unsigned dbg_n = 0, dbg_t = 0;
+#endif
 
   while (node != kEmpty) {
     // ---- inner nodes: one 64-byte record = both children's boxes ----
     while ((unsigned)node < (unsigned)kEmpty) {
+#ifdef NRB_COUNT_VISITS
+      ++dbg_n;
+#endif
       const float4 *np = reinterpret_cast<const float4 *>(sc.nodes + node);
       float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
       int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
@@ -149,6 +159,9 @@ NRB_DI bool traverse(const SceneView &sc, int root, V3 o, V3 d, float tmax, Hit 
       } else {
         const float4 *tp = reinterpret_cast<const float4 *>(sc.tris + first);
         for (uint32_t k = 0; k < cnt; ++k) {
+#ifdef NRB_COUNT_VISITS
+          ++dbg_t;
+#endif
           float4 t0 = __ldg(tp + 3 * k), t1 = __ldg(tp + 3 * k + 1), t2 = __ldg(tp + 3 * k + 2);
           float toi, bv, bw;
           if (cast_tri<ANY>(mk(t0.x, t0.y, t0.z), mk(t1.x, t1.y, t1.z), mk(t2.x, t2.y, t2.z), o, d, tbest, toi, bv, bw)) {
@@ -162,6 +175,12 @@ NRB_DI bool traverse(const SceneView &sc, int root, V3 o, V3 d, float tmax, Hit 
       node = stack[sp--];
     }
   }
+#ifdef NRB_COUNT_VISITS
+  atomicAdd(&g_dbg[0], (unsigned long long)dbg_n);
+  atomicAdd(&g_dbg[1], (unsigned long long)dbg_t);
+  atomicAdd(&g_dbg[2], 1ull);
+  atomicMax(&g_dbg[3], (unsigned long long)(dbg_n + dbg_t));
+#endif
   return found;
 }
 
@@ -265,10 +284,7 @@ NRB_DI bool shadow_candidate(const SceneView &sc, int root, int node_id, V3 o, V
 }
 
 template <bool HAS_SHAPES>
-NRB_DI void shadow_ray(const SceneView &sc, const ShadowQueue &q, uint32_t i, float4 *accum) {
-  float4 a = q.a[i], b = q.b[i];
-  V3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
-  float tmax = a.w;
+NRB_DI void shadow_query(const SceneView &sc, V3 o, V3 d, float tmax, uint32_t pix, V3 contrib, float4 *accum) {
   bool occluded = false;
   V3 filter = mk(1, 1, 1);
   if (HAS_SHAPES) {
@@ -323,10 +339,13 @@ NRB_DI void shadow_ray(const SceneView &sc, const ShadowQueue &q, uint32_t i, fl
       occluded = shadow_candidate<HAS_SHAPES>(sc, cd.root, cd.node, o, d, tmax, filter);
     }
   }
-  if (!occluded) {
-    float4 cc = q.c[i];
-    accum_add(accum, __float_as_uint(b.w), mk(cc.x * filter.x, cc.y * filter.y, cc.z * filter.z));
-  }
+  if (!occluded) accum_add(accum, pix, cmul(contrib, filter));
+}
+
+template <bool HAS_SHAPES>
+NRB_DI void shadow_ray(const SceneView &sc, const ShadowQueue &q, uint32_t i, float4 *accum) {
+  float4 a = q.a[i], b = q.b[i], c = q.c[i];
+  shadow_query<HAS_SHAPES>(sc, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), a.w, __float_as_uint(b.w), mk(c.x, c.y, c.z), accum);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -392,7 +411,7 @@ NRB_DI void drain_closest(const SceneView &sc, const FrameParams &fp, const RayQ
 // PRIMARY: wave 0 generates its rays from the sample slot instead of reading a queue.
 // ---------------------------------------------------------------------------------------------
 template <bool HAS_SHAPES, bool PRIMARY>
-__global__ void __launch_bounds__(kTraceBlock) trace_kernel(SceneView sc, FrameParams fp, RayQueue q, float4 *hits,
+__global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 6 : kTraceMinBlocks) trace_kernel(SceneView sc, FrameParams fp, RayQueue q, float4 *hits,
                                                            WaveCounters *wc_closest, uint32_t slot_lo,
                                                            uint32_t n_slots, ShadowQueue sq, float4 *accum,
                                                            WaveCounters *wc_shadow) {
@@ -408,6 +427,185 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(SceneView sc, FrameP
 // ---------------------------------------------------------------------------------------------
 // K4 — shade + secondary-ray generation (Scene::trace body after the cast, src/scene.rs:168-192)
 // ---------------------------------------------------------------------------------------------
+struct RayState {  // RayWithEnergy (src/ray_with_energy.rs:4-8) + wavefront bookkeeping
+  V3 o, d;
+  float weight, energy, refr;
+  uint32_t gid, path, depth;
+};
+
+NRB_DI RayState load_ray(const RayQueue &q, uint32_t i) {
+  float4 ra = q.a[i], rb = q.b[i], rc = q.c[i];
+  RayState r;
+  r.o = mk(ra.x, ra.y, ra.z), r.d = mk(ra.w, rb.x, rb.y);
+  r.weight = rb.z, r.energy = rb.w, r.refr = rc.x;
+  r.gid = __float_as_uint(rc.y), r.path = __float_as_uint(rc.z), r.depth = __float_as_uint(rc.w);
+  return r;
+}
+
+NRB_DI void store_ray(const RayQueue &q, uint32_t i, const RayState &r) {
+  q.a[i] = make_float4(r.o.x, r.o.y, r.o.z, r.d.x);
+  q.b[i] = make_float4(r.d.y, r.d.z, r.weight, r.energy);
+  q.c[i] = make_float4(r.refr, __uint_as_float(r.gid), __uint_as_float(r.path), __uint_as_float(r.depth));
+}
+
+// Everything the emission steps need about one shaded hit.
+struct Shaded {
+  V3 pt, n;         // hit point, normal facing the ray origin
+  V3 kd, ks;        // Kd (x) texture, Ks
+  float shininess;
+  float w_obj;      // weight of the surface's own colour: w * a' * (1 - mix)
+  float alpha, a1;  // alpha = obj.w * node.alpha; a' = alpha == 1 ? 1 : alpha
+  float refl_mix, refl_att, refr_coeff;
+  uint32_t pix, ipt, smp;
+  bool emit_sh, want_refl, want_refr, trunc_refl, trunc_refr;
+};
+
+// Material evaluation + the combine weights of Scene::trace (src/scene.rs:171-190).  Adds the
+// background (miss) or the ambient term (hit) to the pixel; decides what the ray emits.
+template <bool HAS_SHAPES>
+NRB_DI void shade_eval(const SceneView &sc, const FrameParams &fp, const RayState &r, float4 h, bool active,
+                       float4 *accum, Shaded &out) {
+  const uint32_t prim = __float_as_uint(h.y);
+  out.ipt = r.gid / fp.spp, out.smp = r.gid - out.ipt * fp.spp;
+  out.pix = active ? accum_index(fp, out.ipt) : 0u;
+  const bool is_hit = active && prim != kMiss;
+  if (active && !is_hit) {
+    // miss -> background (src/scene.rs:169)
+    accum_add(accum, out.pix, mk(sc.background[0], sc.background[1], sc.background[2]) * r.weight);
+  }
+  Surface s;
+  s.n = mk(0, 0, 1), s.u = s.v = 0.0f, s.has_uv = false, s.node = 0;
+  NodeInfo ni;
+  ni.material = 0, ni.refl_mix = 0, ni.refl_att = 0, ni.alpha = 1, ni.refr_coeff = 1, ni.flags = 0;
+  float4 tex_color = make_float4(1, 1, 1, 1);
+  float obj_w = 1.0f;
+  V3 obj_rgb = mk(0, 0, 0);
+  bool phong = false;
+  out.pt = mk(0, 0, 0);
+  out.kd = out.ks = mk(0, 0, 0);
+  out.shininess = 0.0f;
+  if (is_hit) {
+    reconstruct<HAS_SHAPES>(sc, r.o, r.d, prim, h.z, h.w, s);
+    out.pt = r.o + r.d * h.x;
+    ni = sc.node_info[s.node];
+    const Material m = sc.materials[ni.material];
+    if (m.kind == NRB_MAT_PHONG) {
+      // PhongMaterial::compute, ambient part (src/phong_material.rs:85-103)
+      phong = true;
+      if (s.has_uv && m.tex >= 0) tex_color = tex_sample(sc, m.tex, s.u, s.v);
+      if (s.has_uv && m.alpha_tex >= 0) obj_w = tex_sample(sc, m.alpha_tex, s.u, s.v).w;
+      obj_rgb = mk(m.ambient[0] * tex_color.x, m.ambient[1] * tex_color.y, m.ambient[2] * tex_color.z);
+      out.kd = mk(m.diffuse[0] * tex_color.x, m.diffuse[1] * tex_color.y, m.diffuse[2] * tex_color.z);
+      out.ks = mk(m.specular[0], m.specular[1], m.specular[2]);
+      out.shininess = m.shininess;
+    } else {
+      float4 c = mat_ambiant(sc, m, s);  // Material::compute default (src/material.rs:8-16)
+      obj_rgb = mk(c.x, c.y, c.z);
+      obj_w = c.w;
+    }
+  }
+  out.n = s.n;
+  // combine weights (src/scene.rs:178-190): out = alpha==1 ? col : col*alpha + refr*(1-alpha),
+  // col = obj*(1-mix) + refl*mix
+  out.alpha = obj_w * ni.alpha;
+  out.a1 = (out.alpha == 1.0f) ? 1.0f : out.alpha;
+  out.w_obj = r.weight * out.a1 * (1.0f - ni.refl_mix);
+  out.refl_mix = ni.refl_mix, out.refl_att = ni.refl_att, out.refr_coeff = ni.refr_coeff;
+  if (is_hit) accum_add(accum, out.pix, obj_rgb * out.w_obj);
+  out.emit_sh = is_hit && phong && sc.shadow_samples > 0;
+  // reflection (Scene::trace_reflection, src/scene.rs:196-218)
+  bool want_refl = is_hit && ni.refl_mix != 0.0f && r.energy > 0.1f;
+  out.trunc_refl = want_refl && (r.depth + 1u >= fp.max_depth);
+  out.want_refl = want_refl && !out.trunc_refl;
+  // refraction (Scene::trace_refraction, src/scene.rs:221-252)
+  bool want_refr = is_hit && out.alpha != 1.0f;
+  out.trunc_refr = want_refr && (r.depth + 1u >= fp.max_depth);
+  out.want_refr = want_refr && !out.trunc_refr;
+}
+
+// One light sample of PhongMaterial::compute (src/phong_material.rs:108-143, src/light.rs:56-63):
+// the shadow segment and the colour it adds if unoccluded (filter applied by the shadow query).
+NRB_DI void light_sample(const SceneView &sc, const FrameParams &fp, const RayState &r, const Shaded &s, int li,
+                         const Light &L, uint32_t k, float inv_ns, V3 &so, V3 &ldir, float &dist, V3 &c) {
+  V3 pos = mk(L.pos[0], L.pos[1], L.pos[2]);
+  if (L.radius != 0.0f) {
+    uint32_t rnd[4];
+    philox4x32_10(s.ipt, s.smp, r.path, ((uint32_t)li << 16) | (k & 0xFFFFu), fp.seed_lo, fp.seed_hi ^ kStreamLight, rnd);
+    pos = pos + mk(u24(rnd[0]), u24(rnd[1]), u24(rnd[2])) * L.radius;
+  }
+  ldir = pos - s.pt;
+  float len = sqrtf(dot(ldir, ldir));
+  ldir = ldir * (1.0f / len);
+  dist = len - 0.001f;
+  float ndl = dot(ldir, s.n);
+  float dcoeff = fmaxf(ndl, 0.0f);
+  c = s.kd * dcoeff;
+  V3 rl = normalize(-ldir + s.n * (2.0f * ndl));
+  float scoeff = -dot(rl, r.d);
+  if (scoeff > 0.0f) c = c + s.ks * powf(scoeff, s.shininess);
+  c = cmul(mk(L.color[0], L.color[1], L.color[2]), c) * (inv_ns * s.w_obj);
+  so = s.pt + ldir * 0.001f;
+}
+
+// Writes the ray's shadow_samples light samples into slots [sbase, sbase + shadow_samples).
+// TRACE_ON_OVERFLOW (tail kernel): a sample that does not fit the queue is traced on the spot.
+template <bool HAS_SHAPES, bool TRACE_ON_OVERFLOW>
+NRB_DI void emit_shadow_rays(const SceneView &sc, const FrameParams &fp, const RayState &r, const Shaded &s,
+                             const ShadowQueue &sq, uint32_t sbase, Counters *ctr, float4 *accum) {
+  uint32_t k_out = 0;
+  for (int li = 0; li < sc.n_lights; ++li) {
+    const Light L = sc.lights[li];
+    uint32_t ns = L.racsample * L.racsample;
+    float inv_ns = 1.0f / (float)ns;
+    for (uint32_t k = 0; k < ns; ++k, ++k_out) {
+      V3 so, ldir, c;
+      float dist;
+      light_sample(sc, fp, r, s, li, L, k, inv_ns, so, ldir, dist, c);
+      uint32_t si = sbase + k_out;
+      if (si < sq.capacity) {
+        sq.a[si] = make_float4(so.x, so.y, so.z, dist);
+        sq.b[si] = make_float4(ldir.x, ldir.y, ldir.z, __uint_as_float(s.pix));
+        sq.c[si] = make_float4(c.x, c.y, c.z, 0.0f);
+      } else if (TRACE_ON_OVERFLOW) {
+        shadow_query<HAS_SHAPES>(sc, so, ldir, dist, s.pix, c, accum);
+      } else {
+        ctr->overflow = 1u;
+      }
+    }
+  }
+}
+
+NRB_DI RayState reflect_ray(const RayState &r, const Shaded &s) {  // src/scene.rs:204-214
+  RayState c;
+  float dn = dot(r.d, s.n);
+  c.d = r.d - s.n * (2.0f * dn);
+  c.o = s.pt + c.d * 0.001f;
+  c.weight = r.weight * s.a1 * s.refl_mix;
+  c.energy = r.energy - s.refl_att;
+  c.refr = r.refr;
+  c.gid = r.gid, c.path = r.path * 2u, c.depth = r.depth + 1u;
+  return c;
+}
+
+NRB_DI RayState refract_ray(const RayState &r, const Shaded &s) {  // src/scene.rs:229-248
+  RayState c;
+  float n1, n2;
+  if (r.refr == 1.0f) {
+    n1 = 1.0f, n2 = s.refr_coeff;
+  } else {
+    n1 = s.refr_coeff, n2 = 1.0f;
+  }
+  V3 along = s.n * dot(r.d, s.n);
+  V3 tangent = r.d - along;
+  c.d = normalize(along + tangent * (n2 / n1));
+  c.o = s.pt + c.d * 0.001f;
+  c.weight = r.weight * (1.0f - s.alpha);
+  c.energy = r.energy;
+  c.refr = n2;
+  c.gid = r.gid, c.path = r.path * 2u + 1u, c.depth = r.depth + 1u;
+  return c;
+}
+
 // Persistent grid; the ray count is read from device memory so the host can enqueue a wave without
 // knowing how many rays the previous one produced.  Queue slots are reserved per BLOCK (warp totals
 // meet in shared memory, one global atomic per block per queue and iteration) and the ray statistics
@@ -417,6 +615,19 @@ struct ShadeShared {
   uint32_t base[2];  // their first slots in the global queues
 };
 
+NRB_DI void flush_stats(Counters *ctr, uint32_t c_shadow, uint32_t c_refl, uint32_t c_refr, uint32_t c_trunc) {
+  c_shadow = __reduce_add_sync(0xFFFFFFFFu, c_shadow);
+  c_refl = __reduce_add_sync(0xFFFFFFFFu, c_refl);
+  c_refr = __reduce_add_sync(0xFFFFFFFFu, c_refr);
+  c_trunc = __reduce_add_sync(0xFFFFFFFFu, c_trunc);
+  if (lane_id() == 0) {
+    if (c_shadow) atomicAdd(&ctr->rays_shadow, (unsigned long long)c_shadow);
+    if (c_refl) atomicAdd(&ctr->rays_reflect, (unsigned long long)c_refl);
+    if (c_refr) atomicAdd(&ctr->rays_refract, (unsigned long long)c_refr);
+    if (c_trunc) atomicAdd(&ctr->paths_truncated, (unsigned long long)c_trunc);
+  }
+}
+
 template <bool HAS_SHAPES, bool PRIMARY>
 __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(SceneView sc, FrameParams fp, RayQueue qin,
                                                                             const float4 *hits, WaveCounters *wc,
@@ -424,7 +635,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
                                                                             uint32_t lo, uint32_t hi, RayQueue qout,
                                                                             ShadowQueue sq, Counters *ctr,
                                                                             float4 *accum) {
-  uint32_t *const tail_out = &wc[1].n_rays;   // next wave's ray count
+  uint32_t *const tail_out = &wc[1].n_rays;  // next wave's ray count
   uint32_t *const tail_shadow = &wc[0].n_shadow;
   __shared__ ShadeShared sm;
   if (threadIdx.x < 2) sm.cnt[threadIdx.x] = 0;
@@ -433,6 +644,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t lane = lane_id();
   const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t S = (uint32_t)sc.shadow_samples;
   uint32_t c_shadow = 0, c_refl = 0, c_refr = 0, c_trunc = 0;
 
   for (uint32_t bb = lo + blockIdx.x * blockDim.x; bb < end; bb += stride) {  // block-uniform trip count
@@ -440,87 +652,30 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
     bool active = i < end;
     float4 h = make_float4(0, 0, 0, 0);
     if (active) h = hits[i];
-    uint32_t prim = __float_as_uint(h.y);
-    V3 o = mk(0, 0, 0), d = mk(0, 0, 1);
-    float weight = 1.0f, energy = 1.0f, refr = 1.0f;
-    uint32_t gid = 0u, path = 1u, depth = 0u;
+    RayState r;
+    r.o = mk(0, 0, 0), r.d = mk(0, 0, 1);
+    r.weight = 1.0f, r.energy = 1.0f, r.refr = 1.0f;  // RayWithEnergy::new (src/ray_with_energy.rs:11-13)
+    r.gid = 0u, r.path = 1u, r.depth = 0u;
     if (PRIMARY) {
-      // RayWithEnergy::new: refr 1.0, energy 1.0 (src/ray_with_energy.rs:11-13); ray regenerated from the slot
-      active = active && prim != kSkip;
-      if (active) primary_ray(fp, slot_lo + i, o, d, gid);
+      active = active && __float_as_uint(h.y) != kSkip;
+      if (active) primary_ray(fp, slot_lo + i, r.o, r.d, r.gid);  // regenerated from the slot, never stored
     } else if (active) {
-      float4 ra = qin.a[i], rb = qin.b[i], rc = qin.c[i];
-      o = mk(ra.x, ra.y, ra.z), d = mk(ra.w, rb.x, rb.y);
-      weight = rb.z, energy = rb.w, refr = rc.x;
-      gid = __float_as_uint(rc.y), path = __float_as_uint(rc.z), depth = __float_as_uint(rc.w);
+      r = load_ray(qin, i);
     }
-    uint32_t ipt = gid / fp.spp, smp = gid - ipt * fp.spp;
-    uint32_t pix = active ? accum_index(fp, ipt) : 0u;
-
-    bool is_hit = active && prim != kMiss;
-    if (active && !is_hit) {
-      // miss -> background (src/scene.rs:169)
-      accum_add(accum, pix, mk(sc.background[0], sc.background[1], sc.background[2]) * weight);
-    }
-
-    // ---- hit: reconstruct the intersection, evaluate the material ------------------------------
-    Surface s;
-    s.n = mk(0, 0, 1), s.u = s.v = 0.0f, s.has_uv = false, s.node = 0;
-    V3 pt = mk(0, 0, 0);
-    NodeInfo ni;
-    ni.material = 0, ni.refl_mix = 0, ni.refl_att = 0, ni.alpha = 1, ni.refr_coeff = 1, ni.flags = 0;
-    Material m;
-    m.kind = NRB_MAT_NORMAL;
-    float4 tex_color = make_float4(1, 1, 1, 1);
-    float obj_w = 1.0f;
-    V3 obj_rgb = mk(0, 0, 0);
-    bool phong = false;
-    if (is_hit) {
-      reconstruct<HAS_SHAPES>(sc, o, d, prim, h.z, h.w, s);
-      pt = o + d * h.x;
-      ni = sc.node_info[s.node];
-      m = sc.materials[ni.material];
-      if (m.kind == NRB_MAT_PHONG) {
-        // PhongMaterial::compute, ambient part (src/phong_material.rs:85-103)
-        phong = true;
-        if (s.has_uv && m.tex >= 0) tex_color = tex_sample(sc, m.tex, s.u, s.v);
-        if (s.has_uv && m.alpha_tex >= 0) obj_w = tex_sample(sc, m.alpha_tex, s.u, s.v).w;
-        obj_rgb = mk(m.ambient[0] * tex_color.x, m.ambient[1] * tex_color.y, m.ambient[2] * tex_color.z);
-      } else {
-        float4 c = mat_ambiant(sc, m, s);  // Material::compute default (src/material.rs:8-16)
-        obj_rgb = mk(c.x, c.y, c.z);
-        obj_w = c.w;
-      }
-    }
-    // combine weights (src/scene.rs:178-190): out = alpha==1 ? col : col*alpha + refr*(1-alpha),
-    // col = obj*(1-mix) + refl*mix
-    float alpha = obj_w * ni.alpha;
-    float a1 = (alpha == 1.0f) ? 1.0f : alpha;
-    float w_obj = weight * a1 * (1.0f - ni.refl_mix);
-    if (is_hit) accum_add(accum, pix, obj_rgb * w_obj);
-
-    // ---- what this ray emits ------------------------------------------------------------------
-    const bool emit_sh = is_hit && phong && sc.shadow_samples > 0;
-    // reflection (Scene::trace_reflection, src/scene.rs:196-218)
-    bool want_refl = is_hit && ni.refl_mix != 0.0f && energy > 0.1f;
-    const bool trunc_refl = want_refl && (depth + 1u >= fp.max_depth);
-    want_refl = want_refl && !trunc_refl;
-    // refraction (Scene::trace_refraction, src/scene.rs:221-252)
-    bool want_refr = is_hit && alpha != 1.0f;
-    const bool trunc_refr = want_refr && (depth + 1u >= fp.max_depth);
-    want_refr = want_refr && !trunc_refr;
-    c_trunc += (trunc_refl ? 1u : 0u) + (trunc_refr ? 1u : 0u);
-    c_refl += want_refl ? 1u : 0u;
-    c_refr += want_refr ? 1u : 0u;
-    c_shadow += emit_sh ? (uint32_t)sc.shadow_samples : 0u;
+    Shaded s;
+    shade_eval<HAS_SHAPES>(sc, fp, r, h, active, accum, s);
+    c_trunc += (s.trunc_refl ? 1u : 0u) + (s.trunc_refr ? 1u : 0u);
+    c_refl += s.want_refl ? 1u : 0u;
+    c_refr += s.want_refr ? 1u : 0u;
+    c_shadow += s.emit_sh ? S : 0u;
 
     // ---- reserve queue slots: warp ballots -> shared-memory totals -> one global atomic per block ----
-    const uint32_t m_sh = __ballot_sync(0xFFFFFFFFu, emit_sh);
-    const uint32_t m_rl = __ballot_sync(0xFFFFFFFFu, want_refl);
-    const uint32_t m_rr = __ballot_sync(0xFFFFFFFFu, want_refr);
+    const uint32_t m_sh = __ballot_sync(0xFFFFFFFFu, s.emit_sh);
+    const uint32_t m_rl = __ballot_sync(0xFFFFFFFFu, s.want_refl);
+    const uint32_t m_rr = __ballot_sync(0xFFFFFFFFu, s.want_refr);
     uint32_t woff_sh = 0, woff_ch = 0;
     if (lane == 0) {
-      uint32_t tsh = __popc(m_sh) * (uint32_t)sc.shadow_samples, tch = __popc(m_rl) + __popc(m_rr);
+      uint32_t tsh = __popc(m_sh) * S, tch = __popc(m_rl) + __popc(m_rr);
       if (tsh) woff_sh = atomicAdd(&sm.cnt[0], tsh);
       if (tch) woff_ch = atomicAdd(&sm.cnt[1], tch);
     }
@@ -535,97 +690,83 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
       sm.cnt[1] = 0;
     }
     __syncthreads();
-    const uint32_t sbase = sm.base[0] + __shfl_sync(0xFFFFFFFFu, woff_sh, 0) + __popc(m_sh & lt_mask) * (uint32_t)sc.shadow_samples;
+    const uint32_t sbase = sm.base[0] + __shfl_sync(0xFFFFFFFFu, woff_sh, 0) + __popc(m_sh & lt_mask) * S;
     const uint32_t cbase = sm.base[1] + __shfl_sync(0xFFFFFFFFu, woff_ch, 0) + __popc(m_rl & lt_mask) + __popc(m_rr & lt_mask);
 
-    // ---- light samples -> shadow rays (src/phong_material.rs:106-147, src/light.rs:56-63) ------
-    if (emit_sh) {
-      uint32_t k_out = 0;
-      for (int li = 0; li < sc.n_lights; ++li) {
-        const Light L = sc.lights[li];
-        uint32_t ns = L.racsample * L.racsample;
-        float inv_ns = 1.0f / (float)ns;
-        for (uint32_t k = 0; k < ns; ++k, ++k_out) {
-          V3 pos = mk(L.pos[0], L.pos[1], L.pos[2]);
-          if (L.radius != 0.0f) {
-            uint32_t rnd[4];
-            philox4x32_10(ipt, smp, path, ((uint32_t)li << 16) | (k & 0xFFFFu), fp.seed_lo, fp.seed_hi ^ kStreamLight, rnd);
-            pos = pos + mk(u24(rnd[0]), u24(rnd[1]), u24(rnd[2])) * L.radius;
-          }
-          V3 ldir = pos - pt;
-          float len = sqrtf(dot(ldir, ldir));
-          ldir = ldir * (1.0f / len);
-          float dist = len - 0.001f;
-          float ndl = dot(ldir, s.n);
-          float dcoeff = fmaxf(ndl, 0.0f);
-          V3 diffuse = mk(m.diffuse[0] * tex_color.x, m.diffuse[1] * tex_color.y, m.diffuse[2] * tex_color.z) * dcoeff;
-          V3 rl = normalize(-ldir + s.n * (2.0f * ndl));
-          float scoeff = -dot(rl, d);
-          V3 c = diffuse;
-          if (scoeff > 0.0f) {
-            float sp = powf(scoeff, m.shininess);
-            c = c + mk(m.specular[0], m.specular[1], m.specular[2]) * sp;
-          }
-          c = cmul(mk(L.color[0], L.color[1], L.color[2]), c) * (inv_ns * w_obj);
-          uint32_t si = sbase + k_out;
-          if (si < sq.capacity) {
-            V3 so = pt + ldir * 0.001f;
-            sq.a[si] = make_float4(so.x, so.y, so.z, dist);
-            sq.b[si] = make_float4(ldir.x, ldir.y, ldir.z, __uint_as_float(pix));
-            sq.c[si] = make_float4(c.x, c.y, c.z, 0.0f);
-          } else {
+    if (s.emit_sh) emit_shadow_rays<HAS_SHAPES, false>(sc, fp, r, s, sq, sbase, ctr, accum);
+    if (s.want_refl) {
+      if (cbase < qout.capacity)
+        store_ray(qout, cbase, reflect_ray(r, s));
+      else
+        ctr->overflow = 1u;
+    }
+    if (s.want_refr) {
+      uint32_t fi = cbase + (s.want_refl ? 1u : 0u);
+      if (fi < qout.capacity)
+        store_ray(qout, fi, refract_ray(r, s));
+      else
+        ctr->overflow = 1u;
+    }
+  }
+  flush_stats(ctr, c_shadow, c_refl, c_refr, c_trunc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tail kernel.  Once a wave is small (a few thousand rays) every further wave costs the latency of its
+// SLOWEST ray plus two launches, and a foliage chain needs ~10 of them.  Here each lane follows its own
+// ray to the end instead — closest hit, shade, next bounce — so the tail costs the longest single
+// chain (max of sums) instead of the sum of per-wave maxima.  Shadow rays are queued and traced by one
+// launch afterwards; when a hit spawns both children the refraction ray is spilled to `qspill`
+// (processed by the next tail launch).
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_SHAPES>
+__global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : 4) tail_kernel(SceneView sc, FrameParams fp, RayQueue qin,
+                                                                              WaveCounters *wc, RayQueue qspill,
+                                                                              ShadowQueue sq, Counters *ctr,
+                                                                              float4 *accum) {
+  const uint32_t lane = lane_id();
+  const uint32_t count = wc[0].n_rays;
+  const uint32_t S = (uint32_t)sc.shadow_samples;
+  uint32_t c_shadow = 0, c_refl = 0, c_refr = 0, c_trunc = 0;
+  while (true) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&wc[0].fetch_closest, 32u);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= count) break;
+    const uint32_t i = base + lane;
+    if (i < count) {
+      RayState r = load_ray(qin, i);
+      while (true) {
+        float4 h = closest_hit<HAS_SHAPES>(sc, r.o, r.d);
+        Shaded s;
+        shade_eval<HAS_SHAPES>(sc, fp, r, h, true, accum, s);
+        c_trunc += (s.trunc_refl ? 1u : 0u) + (s.trunc_refr ? 1u : 0u);
+        if (s.emit_sh) {
+          c_shadow += S;
+          uint32_t sbase = atomicAdd(&wc[0].n_shadow, S);
+          emit_shadow_rays<HAS_SHAPES, true>(sc, fp, r, s, sq, sbase, ctr, accum);
+        }
+        if (s.want_refl && s.want_refr) {
+          ++c_refl, ++c_refr;
+          uint32_t slot = atomicAdd(&wc[1].n_rays, 1u);
+          if (slot < qspill.capacity)
+            store_ray(qspill, slot, refract_ray(r, s));
+          else
             ctr->overflow = 1u;
-          }
-        }
-      }
-    }
-
-    if (want_refl) {
-      uint32_t ri = cbase;
-      if (ri < qout.capacity) {
-        float dn = dot(d, s.n);
-        V3 rdir = d - s.n * (2.0f * dn);
-        V3 ro = pt + rdir * 0.001f;
-        qout.a[ri] = make_float4(ro.x, ro.y, ro.z, rdir.x);
-        qout.b[ri] = make_float4(rdir.y, rdir.z, weight * a1 * ni.refl_mix, energy - ni.refl_att);
-        qout.c[ri] = make_float4(refr, __uint_as_float(gid), __uint_as_float(path * 2u), __uint_as_float(depth + 1u));
-      } else {
-        ctr->overflow = 1u;
-      }
-    }
-    if (want_refr) {
-      uint32_t fi = cbase + (want_refl ? 1u : 0u);
-      if (fi < qout.capacity) {
-        float n1, n2;
-        if (refr == 1.0f) {
-          n1 = 1.0f, n2 = ni.refr_coeff;
+          r = reflect_ray(r, s);
+        } else if (s.want_refl) {
+          ++c_refl;
+          r = reflect_ray(r, s);
+        } else if (s.want_refr) {
+          ++c_refr;
+          r = refract_ray(r, s);
         } else {
-          n1 = ni.refr_coeff, n2 = 1.0f;
+          break;
         }
-        V3 along = s.n * dot(d, s.n);
-        V3 tangent = d - along;
-        V3 nd = normalize(along + tangent * (n2 / n1));
-        V3 no = pt + nd * 0.001f;
-        qout.a[fi] = make_float4(no.x, no.y, no.z, nd.x);
-        qout.b[fi] = make_float4(nd.y, nd.z, weight * (1.0f - alpha), energy);
-        qout.c[fi] = make_float4(n2, __uint_as_float(gid), __uint_as_float(path * 2u + 1u), __uint_as_float(depth + 1u));
-      } else {
-        ctr->overflow = 1u;
       }
     }
   }
-
-  // ---- flush the register statistics: one atomic per warp and counter ----
-  c_shadow = __reduce_add_sync(0xFFFFFFFFu, c_shadow);
-  c_refl = __reduce_add_sync(0xFFFFFFFFu, c_refl);
-  c_refr = __reduce_add_sync(0xFFFFFFFFu, c_refr);
-  c_trunc = __reduce_add_sync(0xFFFFFFFFu, c_trunc);
-  if (lane == 0) {
-    if (c_shadow) atomicAdd(&ctr->rays_shadow, (unsigned long long)c_shadow);
-    if (c_refl) atomicAdd(&ctr->rays_reflect, (unsigned long long)c_refl);
-    if (c_refr) atomicAdd(&ctr->rays_refract, (unsigned long long)c_refr);
-    if (c_trunc) atomicAdd(&ctr->paths_truncated, (unsigned long long)c_trunc);
-  }
+  flush_stats(ctr, c_shadow, c_refl, c_refr, c_trunc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -703,6 +844,14 @@ void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, b
   }
 }
 
+void launch_tail(const SceneView &sc, bool has_shapes, const FrameParams &fp, RayQueue qin, WaveCounters *wc,
+                 RayQueue qspill, ShadowQueue sq, Counters *ctr, float4 *accum, int grid, cudaStream_t st) {
+  if (has_shapes)
+    tail_kernel<true><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum);
+  else
+    tail_kernel<false><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum);
+}
+
 int shade_blocks_per_sm(bool has_shapes) {
   int nb = 0, nb2 = 0;
   if (has_shapes) {
@@ -731,6 +880,18 @@ void launch_untile(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_r
   uint32_t n = width * height;
   uint32_t tiles_x = (width + NRB_TILE - 1) / NRB_TILE;
   untile_kernel<<<(n + 255) / 256, 256, 0, st>>>(gathered, n_ranks, tiles_per_rank, width, height, tiles_x, out_rgb);
+}
+
+void debug_visit_counters(unsigned long long out[4], bool reset) {
+#ifdef NRB_COUNT_VISITS
+  cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 4);
+  if (reset) {
+    unsigned long long z[4] = {0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_dbg, z, sizeof(z));
+  }
+#else
+  out[0] = out[1] = out[2] = out[3] = 0;
+#endif
 }
 
 int trace_blocks_per_sm(bool has_shapes) {

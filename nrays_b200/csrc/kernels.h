@@ -5,7 +5,14 @@
 namespace nrb {
 
 constexpr int kTraceBlock = 128;
-constexpr int kFetchPackets = 2;  // 32-ray packets a warp takes per cursor atomic
+#ifndef NRB_FETCH_PACKETS
+#define NRB_FETCH_PACKETS 2
+#endif
+#ifndef NRB_TRACE_MIN_BLOCKS
+#define NRB_TRACE_MIN_BLOCKS 9
+#endif
+constexpr int kFetchPackets = NRB_FETCH_PACKETS;  // 32-ray packets a warp takes per cursor atomic
+constexpr int kTraceMinBlocks = NRB_TRACE_MIN_BLOCKS;  // resident CTAs / SM the trace kernel is compiled for
 constexpr int kShadeBlock = 128;
 constexpr int kShadeMinBlocks = 6;  // caps shade at 80 registers -> 768 resident threads / SM (8 spills too much)
 
@@ -15,11 +22,14 @@ void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, b
 void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue qin,
                   const float4 *hits, WaveCounters *wc, uint32_t slot_lo, uint32_t n_slots, uint32_t lo, uint32_t hi,
                   RayQueue qout, ShadowQueue sq, Counters *ctr, float4 *accum, int grid, cudaStream_t st);
+void launch_tail(const SceneView &sc, bool has_shapes, const FrameParams &fp, RayQueue qin, WaveCounters *wc,
+                 RayQueue qspill, ShadowQueue sq, Counters *ctr, float4 *accum, int grid, cudaStream_t st);
 int shade_blocks_per_sm(bool has_shapes);
 void launch_resolve(const float4 *accum, uint32_t n, uint32_t spp, float *out_rgb, cudaStream_t st);
 void launch_resolve_rgb8(const float4 *accum, uint32_t n, uint32_t spp, uint8_t *out, cudaStream_t st);
 void launch_untile(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width, uint32_t height,
                    float *out_rgb, cudaStream_t st);
 int trace_blocks_per_sm(bool has_shapes);
+void debug_visit_counters(unsigned long long out[4], bool reset);
 
 }  // namespace nrb
