@@ -213,3 +213,72 @@ def test_tile_sharded_render_equals_full_frame(gpu):
     np.testing.assert_allclose(out.cpu().numpy(), full.cpu().numpy(), rtol=0, atol=2e-6)
     np.testing.assert_allclose(dist.untile_host(packed.cpu().numpy(), world, w, h).reshape(-1), full.cpu().numpy(), atol=2e-6)
     scene.close()
+
+
+# ---- driver paths that the default sizes never reach -------------------------------------------------
+class _Env:
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        import os
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        import os
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _glass_mirror_scene():
+    """Nodes that spawn BOTH children (refl_mix > 0 and alpha < 1): the tail kernel must spill one."""
+    nodes = [node(Ball(0.9), phong(ka=(0.2, 0.1, 0.1)), pos=(-1.2, 0, 0), alpha=0.4, refr=1.2, refl=(0.3, 0.3)),
+             node(Cuboid((0.7, 0.7, 0.7)), phong(ka=(0.1, 0.2, 0.1)), pos=(1.2, 0, 0.5), angle=(0, 30, 0), alpha=0.5, refr=1.1, refl=(0.25, 0.4)),
+             node(Plane((0, 1, 0)), phong(), pos=(0, -1.0, 0), refl=(0.3, 0.3))]
+    lights = [Light((1.0, 4.0, -2.0), 0.4, 10, (1, 1, 1))]   # 9 samples per hit
+    return nodes, lights
+
+
+def test_both_children_spill_and_area_light(gpu):
+    nodes, lights = _glass_mirror_scene()
+    img, st, ref, ost = render_both(nodes, lights, eye=(0, 1.5, -5.5), w=128, h=96, spp=2, window=1.0, seed=3)
+    assert_parity(img, ref, max_frac=2e-3, what="both children")
+    assert_counts_close(st, ost)
+    assert st.rays_reflect > 0 and st.rays_refract > 0
+
+
+@pytest.mark.parametrize("env", [dict(NRB_TAIL_RAYS=0), dict(NRB_TAIL_RAYS=1 << 30), dict(NRB_SHADOW_CAP=4096),
+                                 dict(NRB_BATCH_SLOTS=4096), dict(NRB_BATCH_SLOTS=4096, NRB_SHADOW_CAP=2048, NRB_TAIL_RAYS=64)])
+def test_driver_paths_give_the_same_image(gpu, env):
+    """No tail / everything in the tail / chunked shadow queue / many batches: same frame as the default path."""
+    nodes, lights = _glass_mirror_scene()
+    base, st0, ref, ost = render_both(nodes, lights, eye=(0, 1.5, -5.5), w=96, h=80, spp=2, window=1.0, seed=8)
+    with _Env(**env):
+        img, st, _, _ = render_both(nodes, lights, eye=(0, 1.5, -5.5), w=96, h=80, spp=2, window=1.0, seed=8)
+    np.testing.assert_allclose(img, base, rtol=0, atol=3e-5)   # only the order of float atomics may differ
+    assert st.as_dict()["rays_total"] == st0.as_dict()["rays_total"]
+    assert_parity(img, ref, max_frac=2e-3, what=str(env))
+
+
+def test_mesh_scene_driver_paths(gpu):
+    scene, camd, cfg = configs.build("C3", target_tris=30000, lod=4)
+    w, h = 160, 90
+    cam = make_camera(w, h, 2, 1.0, camd.eye, camd.projection((w, h)), seed=2)
+
+    def go():
+        out = np.empty((w * h, 3), np.float32)
+        st = A.NrbStats()
+        _lib.check(gpu.nrb_render(scene.handle, C.byref(cam), out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(st)))
+        return out, st
+
+    base, st0 = go()
+    for env in (dict(NRB_TAIL_RAYS=0), dict(NRB_TAIL_RAYS=1 << 30), dict(NRB_BATCH_SLOTS=8192), dict(NRB_SHADOW_CAP=1024)):
+        with _Env(**env):
+            img, st = go()
+        np.testing.assert_allclose(img, base, rtol=0, atol=3e-5, err_msg=str(env))
+        assert st.as_dict()["rays_total"] == st0.as_dict()["rays_total"], env
+    scene.close()
