@@ -190,6 +190,16 @@ int nrb_device_count(void);
  * loader3d.rs:695), uploads everything to `device`.  The descriptor is not retained. */
 int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out);
 
+/* Host-only half of nrb_scene_create: validates the tables and builds the BVH WITHOUT touching a
+ * device (same status codes for malformed input), then checks the tree's structural invariants.
+ * Lets a host validate a flattened scene, and the CPU test-suite exercise the builder. */
+typedef struct NrbBuildInfo {
+  uint64_t bvh_nodes, triangles, shapes, planes, transparent_candidates;
+  uint32_t max_depth; /* deepest leaf, <= 60 (traversal stack) */
+  float build_ms;
+} NrbBuildInfo;
+int nrb_scene_validate(const NrbSceneDesc *desc, NrbBuildInfo *info);
+
 /* Drops the handle and all device memory. */
 void nrb_scene_destroy(NrbScene *scene);
 

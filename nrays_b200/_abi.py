@@ -156,10 +156,23 @@ class NrbStats(C.Structure):
         return d
 
 
+class NrbBuildInfo(C.Structure):
+    _fields_ = [
+        ("bvh_nodes", C.c_uint64),
+        ("triangles", C.c_uint64),
+        ("shapes", C.c_uint64),
+        ("planes", C.c_uint64),
+        ("transparent_candidates", C.c_uint64),
+        ("max_depth", C.c_uint32),
+        ("build_ms", C.c_float),
+    ]
+
+
 # Every symbol include/nrays_b200.h declares (tests check the .so exports all of them).
 EXPORTS = [
     "nrb_device_count",
     "nrb_scene_create",
+    "nrb_scene_validate",
     "nrb_scene_destroy",
     "nrb_scene_set_background",
     "nrb_scene_set_stream",

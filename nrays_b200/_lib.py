@@ -31,6 +31,8 @@ def load():
     lib.nrb_device_count.restype = C.c_int
     lib.nrb_scene_create.argtypes = [C.POINTER(A.NrbSceneDesc), C.c_int, C.POINTER(vp)]
     lib.nrb_scene_create.restype = C.c_int
+    lib.nrb_scene_validate.argtypes = [C.POINTER(A.NrbSceneDesc), C.POINTER(A.NrbBuildInfo)]
+    lib.nrb_scene_validate.restype = C.c_int
     lib.nrb_scene_destroy.argtypes = [vp]
     lib.nrb_scene_destroy.restype = None
     lib.nrb_scene_set_background.argtypes = [vp, C.POINTER(C.c_float)]

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -146,7 +147,25 @@ int relayout_bfs(std::vector<BvhNode> &nodes, int &root_all, int &root_opaque, s
   return 0;
 }
 
-int build_scene(const NrbSceneDesc &d, NrbScene &S) {
+// Host-side result of Scene::new: validated tables + BVH, ready to upload.
+struct HostScene {
+  std::vector<BvhNode> nodes;
+  std::vector<Tri> tris;
+  std::vector<TriUV> tri_uvs;
+  std::vector<Shape> shapes;
+  std::vector<NodeInfo> node_info;
+  std::vector<Material> materials;
+  std::vector<Texture> textures;
+  std::vector<Light> lights;
+  std::vector<int> planes;
+  std::vector<Candidate> candidates;
+  int root_all = kEmpty, root_opaque = kEmpty;
+  int shadow_samples = 0;
+  bool any_refl = false, any_refr = false;
+  int depth_tri = 0, depth_mid = 0, depth_top = 0;
+};
+
+int flatten_scene(const NrbSceneDesc &d, HostScene &H) {
   if (d.n_nodes && !d.nodes) return fail(NRB_ERR_INVALID_ARG, "nodes is NULL");
   if (d.n_lights && !d.lights) return fail(NRB_ERR_INVALID_ARG, "lights is NULL");
   if (d.n_materials && !d.materials) return fail(NRB_ERR_INVALID_ARG, "materials is NULL");
@@ -412,23 +431,87 @@ int build_scene(const NrbSceneDesc &d, NrbScene &S) {
   relayout_bfs(bb.nodes, root_all, root_opaque, candidates);
 
   // leaf-ordered triangle arrays
-  std::vector<Tri> tris(bb.tri_order.size());
-  std::vector<TriUV> tri_uvs(bb.tri_order.size());
-  for (size_t k = 0; k < bb.tri_order.size(); ++k) tris[k] = tris_in[bb.tri_order[k]], tri_uvs[k] = uvs_in[bb.tri_order[k]];
-  std::vector<Tri>().swap(tris_in);
-  std::vector<TriUV>().swap(uvs_in);
+  H.tris.resize(bb.tri_order.size());
+  H.tri_uvs.resize(bb.tri_order.size());
+  for (size_t k = 0; k < bb.tri_order.size(); ++k) H.tris[k] = tris_in[bb.tri_order[k]], H.tri_uvs[k] = uvs_in[bb.tri_order[k]];
+  H.nodes.swap(bb.nodes);
+  H.shapes.swap(shapes);
+  H.node_info.swap(node_info);
+  H.materials.swap(materials);
+  H.textures.swap(textures);
+  H.lights.swap(lights);
+  H.planes.swap(planes);
+  H.candidates.swap(candidates);
+  H.root_all = root_all, H.root_opaque = root_opaque;
+  H.shadow_samples = shadow_samples;
+  H.any_refl = any_refl, H.any_refr = any_refr;
+  H.depth_tri = depth_tri, H.depth_mid = depth_mid, H.depth_top = depth_top;
+  return NRB_OK;
+}
 
-  // ---- upload ---------------------------------------------------------------------------------
-  CU(upload(S.d_nodes, bb.nodes));
-  CU(upload(S.d_tris, tris));
-  CU(upload(S.d_tri_uvs, tri_uvs));
-  CU(upload(S.d_shapes, shapes));
-  CU(upload(S.d_node_info, node_info));
-  CU(upload(S.d_materials, materials));
-  CU(upload(S.d_textures, textures));
-  CU(upload(S.d_lights, lights));
-  CU(upload(S.d_planes, planes));
-  CU(upload(S.d_candidates, candidates));
+// Structural self-check of the built BVH (used by nrb_scene_validate): every triangle sits in exactly one
+// leaf, every child box contains what is below it, every node is reachable exactly once.
+int check_bvh(const HostScene &H, std::string &why) {
+  std::vector<char> tri_seen(H.tris.size(), 0), node_seen(H.nodes.size(), 0);
+  struct Item {
+    int code;
+    Box box;
+    bool has_box;
+  };
+  std::vector<Item> stack;
+  if (H.root_all != kEmpty) stack.push_back(Item{H.root_all, Box{}, false});
+  auto inside = [](const Box &outer, const Box &inner) {
+    for (int k = 0; k < 3; ++k)
+      if (inner.lo[k] < outer.lo[k] || inner.hi[k] > outer.hi[k]) return false;
+    return true;
+  };
+  while (!stack.empty()) {
+    Item it = stack.back();
+    stack.pop_back();
+    if (it.code >= 0) {
+      if ((size_t)it.code >= H.nodes.size()) return why = "child index out of range", 1;
+      if (node_seen[it.code]++) return why = "node reachable twice", 1;
+      const BvhNode &n = H.nodes[it.code];
+      Box b0{{n.n0.x, n.n0.z, n.n2.x}, {n.n0.y, n.n0.w, n.n2.y}}, b1{{n.n1.x, n.n1.z, n.n2.z}, {n.n1.y, n.n1.w, n.n2.w}};
+      if (it.has_box && (!inside(it.box, b0) || !inside(it.box, b1))) return why = "child box outside its parent box", 1;
+      stack.push_back(Item{n.n3.x, b0, true});
+      stack.push_back(Item{n.n3.y, b1, true});
+    } else {
+      uint32_t code = (uint32_t)~it.code, first = code >> 3, cnt = ((code >> 1) & 3u) + 1u;
+      if (code & 1u) {
+        if (first >= H.shapes.size()) return why = "shape leaf out of range", 1;
+        continue;
+      }
+      for (uint32_t k = 0; k < cnt; ++k) {
+        if (first + k >= H.tris.size()) return why = "triangle leaf out of range", 1;
+        if (tri_seen[first + k]++) return why = "triangle in two leaves", 1;
+        const Tri &t = H.tris[first + k];
+        float v[3][3] = {{t.t0.x, t.t0.y, t.t0.z}, {t.t0.x + t.t1.x, t.t0.y + t.t1.y, t.t0.z + t.t1.z}, {t.t0.x + t.t2.x, t.t0.y + t.t2.y, t.t0.z + t.t2.z}};
+        if (it.has_box)
+          for (auto &p : v)
+            for (int a = 0; a < 3; ++a)
+              if (p[a] < it.box.lo[a] || p[a] > it.box.hi[a]) return why = "triangle vertex outside its leaf box", 1;
+      }
+    }
+  }
+  for (char c : tri_seen)
+    if (!c) return why = "triangle not referenced by any leaf", 1;
+  for (char c : node_seen)
+    if (!c) return why = "unreachable node", 1;
+  return 0;
+}
+
+int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
+  CU(upload(S.d_nodes, H.nodes));
+  CU(upload(S.d_tris, H.tris));
+  CU(upload(S.d_tri_uvs, H.tri_uvs));
+  CU(upload(S.d_shapes, H.shapes));
+  CU(upload(S.d_node_info, H.node_info));
+  CU(upload(S.d_materials, H.materials));
+  CU(upload(S.d_textures, H.textures));
+  CU(upload(S.d_lights, H.lights));
+  CU(upload(S.d_planes, H.planes));
+  CU(upload(S.d_candidates, H.candidates));
   {
     size_t tb = std::max<size_t>(d.n_texels * 16, 16);
     CU(S.d_texels.ensure(tb));
@@ -446,19 +529,19 @@ int build_scene(const NrbSceneDesc &d, NrbScene &S) {
   v.lights = S.d_lights.as<Light>();
   v.planes = S.d_planes.as<int>();
   v.candidates = S.d_candidates.as<Candidate>();
-  v.root_all = root_all;
-  v.root_opaque = root_opaque;
-  v.n_planes = (int)planes.size();
-  v.n_candidates = (int)candidates.size();
-  v.n_lights = (int)lights.size();
-  v.shadow_samples = shadow_samples;
+  v.root_all = H.root_all;
+  v.root_opaque = H.root_opaque;
+  v.n_planes = (int)H.planes.size();
+  v.n_candidates = (int)H.candidates.size();
+  v.n_lights = (int)H.lights.size();
+  v.shadow_samples = H.shadow_samples;
   for (int k = 0; k < 3; ++k) v.background[k] = d.background[k];
-  S.has_shapes = !shapes.empty();
-  S.child_factor = (any_refl ? 1 : 0) + (any_refr ? 1 : 0);
-  S.n_bvh_nodes = bb.nodes.size();
-  S.n_tris = tris.size();
-  S.scene_bytes = bb.nodes.size() * sizeof(BvhNode) + tris.size() * (sizeof(Tri) + sizeof(TriUV)) +
-                  shapes.size() * sizeof(Shape) + d.n_texels * 16;
+  S.has_shapes = !H.shapes.empty();
+  S.child_factor = (H.any_refl ? 1 : 0) + (H.any_refr ? 1 : 0);
+  S.n_bvh_nodes = H.nodes.size();
+  S.n_tris = H.tris.size();
+  S.scene_bytes = H.nodes.size() * sizeof(BvhNode) + H.tris.size() * (sizeof(Tri) + sizeof(TriUV)) +
+                  H.shapes.size() * sizeof(Shape) + d.n_texels * 16;
   return NRB_OK;
 }
 
@@ -858,7 +941,10 @@ int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out) {
   CU(cudaEventCreate(&S->ev_end));
   CU(cudaHostAlloc((void **)&S->h_counters, sizeof(Counters), cudaHostAllocDefault));
   CU(S->d_counters.ensure(sizeof(Counters)));
-  int rc = build_scene(*desc, *S);
+  HostScene H;
+  int rc = flatten_scene(*desc, H);
+  if (rc) return rc;
+  rc = upload_scene(*desc, H, *S);
   if (rc) return rc;
   S->grid_trace = S->sm_count * trace_blocks_per_sm(S->has_shapes);
   S->grid_tail = S->sm_count * 4;
@@ -868,6 +954,30 @@ int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out) {
 }
 
 void nrb_scene_destroy(NrbScene *scene) { delete scene; }
+
+int nrb_scene_validate(const NrbSceneDesc *desc, NrbBuildInfo *info) {
+  if (!desc) return fail(NRB_ERR_INVALID_ARG, "desc is NULL");
+  if (desc->struct_size != sizeof(NrbSceneDesc) || desc->abi_version != NRB_ABI_VERSION)
+    return fail(NRB_ERR_INVALID_ARG, "NrbSceneDesc struct_size / abi_version mismatch");
+  HostScene H;
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = flatten_scene(*desc, H);
+  if (rc) return rc;
+  double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  std::string why;
+  if (check_bvh(H, why)) return fail(NRB_ERR_CUDA + 100, "internal BVH invariant violated: " + why);
+  if (info) {
+    std::memset(info, 0, sizeof(*info));
+    info->bvh_nodes = H.nodes.size();
+    info->triangles = H.tris.size();
+    info->shapes = H.shapes.size();
+    info->planes = H.planes.size();
+    info->transparent_candidates = H.candidates.size();
+    info->max_depth = (uint32_t)(H.depth_tri + H.depth_mid + H.depth_top);
+    info->build_ms = (float)ms;
+  }
+  return NRB_OK;
+}
 
 int nrb_scene_set_background(NrbScene *scene, const float rgb[3]) {
   if (!scene || !rgb) return fail(NRB_ERR_INVALID_ARG, "scene/rgb is NULL");

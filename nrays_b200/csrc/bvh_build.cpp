@@ -2,9 +2,11 @@
 #include "bvh_build.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace nrb {
 
@@ -38,10 +40,71 @@ void pad_box(Box &b, float scene_extent) {
   }
 }
 
+// Placeholder child codes for deferred subtrees: inner-node indices never get this large.
+static constexpr int kPlaceholderBase = 0x40000000;
+
 int BvhBuilder::build_triangles(std::vector<BuildItem> &items, Box *root_box) {
   if (const char *e = getenv("NRB_BVH_CNODE")) kCostNode = (float)atof(e);
   if (const char *e = getenv("NRB_BVH_LEAF")) kLeafMax = std::max(1, std::min(kMaxLeafTris, atoi(e)));
-  return build_rec(items.data(), items.size(), false, 0, root_box);
+  unsigned hw = std::thread::hardware_concurrency();
+  if (const char *e = getenv("NRB_BVH_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+  if (items.size() < 200000 || hw < 2) return build_rec(items.data(), items.size(), false, 0, root_box);
+
+  // Large mesh: split the top of the tree here, build the subtrees (<= n / (8 * threads) triangles each)
+  // on worker threads into private pools, then splice them into the shared pool.
+  std::vector<Task> tasks;
+  tasks_ = &tasks;
+  task_size_ = std::max<size_t>(16384, items.size() / (8 * (size_t)hw));
+  int root = build_rec(items.data(), items.size(), false, 0, root_box);
+  tasks_ = nullptr;
+  std::vector<BvhBuilder> subs(tasks.size());
+  std::vector<int> sub_root(tasks.size());
+  std::vector<int> sub_depth(tasks.size(), 0);
+  {
+    std::atomic<size_t> next(0);
+    auto worker = [&]() {
+      for (;;) {
+        size_t i = next.fetch_add(1);
+        if (i >= tasks.size()) return;
+        Box b;
+        sub_root[i] = subs[i].build_rec(tasks[i].items, tasks[i].n, false, tasks[i].depth, &b);
+        sub_depth[i] = subs[i].max_depth_seen;
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < std::min<unsigned>(hw, (unsigned)tasks.size()); ++t) pool.emplace_back(worker);
+    for (auto &t : pool) t.join();
+  }
+  // splice: shift node indices and leaf triangle offsets of each private pool
+  std::vector<int> resolved(tasks.size());
+  for (size_t i = 0; i < tasks.size(); ++i) {
+    const int node_off = (int)nodes.size();
+    const uint32_t tri_off = (uint32_t)tri_order.size();
+    auto shift = [&](int c) -> int {
+      if (c >= 0) return c + node_off;
+      uint32_t code = (uint32_t)~c;
+      uint32_t first = (code >> 3) + tri_off;
+      return ~(int)((first << 3) | (code & 7u));
+    };
+    for (BvhNode n : subs[i].nodes) {
+      n.n3.x = shift(n.n3.x);
+      n.n3.y = shift(n.n3.y);
+      nodes.push_back(n);
+    }
+    tri_order.insert(tri_order.end(), subs[i].tri_order.begin(), subs[i].tri_order.end());
+    resolved[i] = shift(sub_root[i]);
+    max_depth_seen = std::max(max_depth_seen, sub_depth[i]);
+    subs[i] = BvhBuilder();
+  }
+  auto fix = [&](int &c) {
+    if (c >= kPlaceholderBase && c != kEmpty) c = resolved[c - kPlaceholderBase];
+  };
+  for (auto &n : nodes) {
+    fix(n.n3.x);
+    fix(n.n3.y);
+  }
+  fix(root);
+  return root;
 }
 
 int BvhBuilder::build_payloads(std::vector<BuildItem> &items, Box *root_box) {
@@ -69,6 +132,12 @@ int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, B
 
   size_t max_leaf = payload ? 1 : (size_t)kLeafMax;
   if (n == 1) return make_leaf_node();
+  if (tasks_ && n <= task_size_ && depth > 0) {
+    // small enough: build this subtree on a worker thread
+    int ph = kPlaceholderBase + (int)tasks_->size();
+    tasks_->push_back(Task{items, n, depth, ph});
+    return ph;
+  }
 
   // ---- choose a split ---------------------------------------------------------------------
   int best_axis = -1, best_bin = -1;

@@ -52,7 +52,15 @@ struct BvhBuilder {
   int build_payloads(std::vector<BuildItem> &items, Box *root_box);
 
  private:
+  struct Task {
+    BuildItem *items;
+    size_t n;
+    int depth;
+    int placeholder;  // child code written into the parent until the subtree is merged
+  };
   int build_rec(BuildItem *items, size_t n, bool payload, int depth, Box *out_box);
+  std::vector<Task> *tasks_ = nullptr;  // non-null while the top of a large tree is being split
+  size_t task_size_ = 0;
 };
 
 // widen a box by a few ulps so f32 slab tests stay conservative w.r.t. the triangle test
