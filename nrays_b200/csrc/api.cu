@@ -661,7 +661,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   const uint64_t shadow_cap_req = env_size("NRB_SHADOW_CAP", 16u << 20);
   const uint64_t mem_ceiling = env_size("NRB_QUEUE_BYTES", 64ull << 30);
   const uint32_t S_total = (uint32_t)S.view.shadow_samples;
-  const uint64_t tail_threshold = env_size("NRB_TAIL_RAYS", 1u << 20);
+  const uint64_t tail_threshold = env_size("NRB_TAIL_RAYS", 4u << 20);
   uint64_t primary = 0;
 
   const size_t wc_len = (size_t)fp.max_depth + 3;

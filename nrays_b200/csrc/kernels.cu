@@ -651,11 +651,11 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
     const uint32_t i = bb + threadIdx.x;
     bool active = i < end;
     float4 h = make_float4(0, 0, 0, 0);
-    if (active) h = hits[i];
     RayState r;
     r.o = mk(0, 0, 0), r.d = mk(0, 0, 1);
     r.weight = 1.0f, r.energy = 1.0f, r.refr = 1.0f;  // RayWithEnergy::new (src/ray_with_energy.rs:11-13)
     r.gid = 0u, r.path = 1u, r.depth = 0u;
+    if (active) h = hits[i];
     if (PRIMARY) {
       active = active && __float_as_uint(h.y) != kSkip;
       if (active) primary_ray(fp, slot_lo + i, r.o, r.d, r.gid);  // regenerated from the slot, never stored
