@@ -103,8 +103,11 @@ class AssetResolver:
     def read_text(self, path):
         if path in self.files:
             return self.files[path]
-        with open(os.path.join(self.base_dir, path), "r") as f:
-            return f.read()
+        try:
+            with open(os.path.join(self.base_dir, path), "r") as f:
+                return f.read()
+        except OSError as e:
+            raise OSError("cannot read %s: %s" % (path, e))
 
     def texture(self, path, opacity):
         """Texture2d::from_png(path, opacity, Bilinear, Wrap) with the per-path cache of
@@ -123,10 +126,18 @@ class AssetResolver:
         return t
 
     def obj(self, objpath, mtldir):
+        """obj::parse_file(objpath, mtldir, "") — loader3d.rs:662.  Registered stand-ins first, then OBJ text
+        registered under `files`, then the file system."""
         if objpath in self.objs:
             return self.objs[objpath]
-        raise SceneFileError(
-            "OBJ file %s is not available (media/ is not part of the reference tree); register a stand-in" % objpath)
+        from . import obj as objmod
+
+        if objpath in self.files:
+            return objmod.parse(self.files[objpath], lambda name: self.read_text(os.path.join(mtldir, name)), "")
+        full = os.path.join(self.base_dir, objpath)
+        if not os.path.exists(full):
+            raise SceneFileError("OBJ file %s not found (scenes/media/ is not part of the reference tree)" % objpath)
+        return objmod.parse_file(full, os.path.join(self.base_dir, mtldir), "")
 
 
 class Camera:
