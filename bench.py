@@ -260,6 +260,14 @@ def run_ours(args, rank, local_rank, world):
             td.all_reduce(r, op=td.ReduceOp.SUM)
         return float(t.item()), float(r.item())
 
+    def reduce_counts(stats):
+        keys = ("rays_primary", "rays_reflect", "rays_refract", "rays_shadow")
+        t = torch.tensor([float(sum(s[k] for s, _ in stats)) for k in keys], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.SUM)
+        return dict(zip(keys, [float(x) for x in t.tolist()]))
+
+    counts_all = reduce_counts(stats_dev)   # whole job (all ranks), for the frame-level roofline
     ms_dev_max, rays_dev = reduce(ms_dev, stats_dev)
     ms_e2e_max, rays_e2e = reduce(ms_e2e, stats_e2e)
     launches = sum(s["kernel_launches"] + extra for s, extra in stats_dev)
@@ -283,8 +291,9 @@ def run_ours(args, rank, local_rank, world):
         per_ray = None
         bytes_k = 16 * n_primary_k + 48 * (n_closest - n_primary_k) + 64 * n_shadow + l_k * geom_bytes
         achieved = bytes_k / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
-        n_primary = sum(s["rays_primary"] for s, _ in stats_dev)
-        frame_bytes = 160 * (n_closest + n_shadow) + 16 * n_primary + len(stats_dev) * s0["scene_bytes"]
+        # frame-level figure of SURVEY 8d over the WHOLE job: 160 B per ray + 16 B per primary + the scene once per rank and frame
+        n_all = sum(counts_all.values())
+        frame_bytes = 160 * n_all + 16 * counts_all["rays_primary"] + world * len(stats_dev) * s0["scene_bytes"]
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -298,7 +307,8 @@ def run_ours(args, rank, local_rank, world):
             "bytes_per_launch": bytes_k / max(1, l_k), "ms_per_launch": ms_k / max(1, l_k),
             "kernel_share_of_step": ms_k / ms_dev if ms_dev > 0 else None,
             "frame": {"algorithmic_bytes_per_step": frame_bytes / len(stats_dev),
-                      "achieved": frame_bytes / (ms_dev_max * 1e-3) / 1e9, "frac": frame_bytes / (ms_dev_max * 1e-3) / 1e9 / peak},
+                      "achieved": frame_bytes / (ms_dev_max * 1e-3) / 1e9, "peak": peak * world,
+                      "frac": frame_bytes / (ms_dev_max * 1e-3) / 1e9 / (peak * world)},
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
