@@ -195,10 +195,29 @@ int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out);
  * Lets a host validate a flattened scene, and the CPU test-suite exercise the builder. */
 typedef struct NrbBuildInfo {
   uint64_t bvh_nodes, triangles, shapes, planes, transparent_candidates;
-  uint32_t max_depth; /* deepest leaf, <= 60 (traversal stack) */
-  float build_ms;
+  uint32_t max_depth;  /* deepest leaf, <= 60 (traversal stack) */
+  float build_ms;      /* host wall time of flatten + BVH build (+ upload for nrb_scene_create*) */
+  float gpu_build_ms;  /* CUDA-event time of the device build kernels (NRB_BUILDER_LBVH), else 0 */
+  uint32_t builder;    /* NRB_BUILDER_* actually used */
 } NrbBuildInfo;
 int nrb_scene_validate(const NrbSceneDesc *desc, NrbBuildInfo *info);
+
+/* BVH builders.  The tree shape never changes render results, only build and traversal cost. */
+enum {
+  NRB_BUILDER_SAH = 0, /* host binned-SAH build (threaded): best traversal, default */
+  NRB_BUILDER_LBVH = 1 /* device build (Morton sort + Karras radix tree + bottom-up fit): ~100x faster to build,
+                          slower to traverse — for one-shot renders of large meshes / dynamic scenes */
+};
+typedef struct NrbBuildOptions {
+  uint32_t builder; /* NRB_BUILDER_* */
+  uint32_t _reserved[3];
+} NrbBuildOptions;
+
+/* nrb_scene_create with options (NULL = defaults).  Env NRB_BUILDER=sah|lbvh overrides, for experiments. */
+int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOptions *opts, NrbScene **out);
+
+/* How the scene behind a handle was built. */
+int nrb_scene_build_info(const NrbScene *scene, NrbBuildInfo *info);
 
 /* Drops the handle and all device memory. */
 void nrb_scene_destroy(NrbScene *scene);

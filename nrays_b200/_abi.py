@@ -165,13 +165,25 @@ class NrbBuildInfo(C.Structure):
         ("transparent_candidates", C.c_uint64),
         ("max_depth", C.c_uint32),
         ("build_ms", C.c_float),
+        ("gpu_build_ms", C.c_float),
+        ("builder", C.c_uint32),
     ]
+
+
+class NrbBuildOptions(C.Structure):
+    _fields_ = [("builder", C.c_uint32), ("_reserved", C.c_uint32 * 3)]
+
+
+NRB_BUILDER_SAH = 0
+NRB_BUILDER_LBVH = 1
 
 
 # Every symbol include/nrays_b200.h declares (tests check the .so exports all of them).
 EXPORTS = [
     "nrb_device_count",
     "nrb_scene_create",
+    "nrb_scene_create_opts",
+    "nrb_scene_build_info",
     "nrb_scene_validate",
     "nrb_scene_destroy",
     "nrb_scene_set_background",

@@ -31,6 +31,10 @@ def load():
     lib.nrb_device_count.restype = C.c_int
     lib.nrb_scene_create.argtypes = [C.POINTER(A.NrbSceneDesc), C.c_int, C.POINTER(vp)]
     lib.nrb_scene_create.restype = C.c_int
+    lib.nrb_scene_create_opts.argtypes = [C.POINTER(A.NrbSceneDesc), C.c_int, C.POINTER(A.NrbBuildOptions), C.POINTER(vp)]
+    lib.nrb_scene_create_opts.restype = C.c_int
+    lib.nrb_scene_build_info.argtypes = [vp, C.POINTER(A.NrbBuildInfo)]
+    lib.nrb_scene_build_info.restype = C.c_int
     lib.nrb_scene_validate.argtypes = [C.POINTER(A.NrbSceneDesc), C.POINTER(A.NrbBuildInfo)]
     lib.nrb_scene_validate.restype = C.c_int
     lib.nrb_scene_destroy.argtypes = [vp]

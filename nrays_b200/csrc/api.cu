@@ -14,6 +14,7 @@
 #include "../../include/nrays_b200.h"
 #include "bvh_build.h"
 #include "kernels.h"
+#include "lbvh.h"
 
 using namespace nrb;
 
@@ -85,6 +86,7 @@ struct NrbScene {
   int child_factor = 0;  // max secondary rays per ray (reflection + refraction possible in this scene)
   uint64_t n_bvh_nodes = 0, n_tris = 0, scene_bytes = 0;
   int grid_trace = 148, grid_tail = 148;
+  NrbBuildInfo build_info{};
   // frame state
   DevBuf d_q[2][3], d_hits, d_sq[3], d_accum, d_counters, d_wave, d_out, d_out8;
   uint32_t q_cap[2] = {0, 0}, sq_cap = 0, hits_cap = 0;
@@ -163,9 +165,10 @@ struct HostScene {
   int shadow_samples = 0;
   bool any_refl = false, any_refr = false;
   int depth_tri = 0, depth_mid = 0, depth_top = 0;
+  float gpu_build_ms = 0.0f;  // device time of the LBVH kernels (NRB_BUILDER_LBVH)
 };
 
-int flatten_scene(const NrbSceneDesc &d, HostScene &H) {
+int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BUILDER_SAH) {
   if (d.n_nodes && !d.nodes) return fail(NRB_ERR_INVALID_ARG, "nodes is NULL");
   if (d.n_lights && !d.lights) return fail(NRB_ERR_INVALID_ARG, "lights is NULL");
   if (d.n_materials && !d.materials) return fail(NRB_ERR_INVALID_ARG, "materials is NULL");
@@ -365,6 +368,38 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H) {
   bb.nodes.reserve(total_tris / 2 + 16);
   bb.tri_order.reserve(total_tris);
   std::vector<BuildItem> opaque_items, top_items;
+  // builds one tree over a set of triangles with the selected builder and appends it to the shared pools
+  auto build_set = [&](std::vector<BuildItem> &items, Box *rb, int *code) -> int {
+    if (builder == NRB_BUILDER_LBVH) {
+      std::vector<Box> boxes(items.size());
+      for (size_t k = 0; k < items.size(); ++k) boxes[k] = items[k].box;
+      std::vector<BvhNode> sub;
+      std::vector<uint32_t> order;
+      int depth = 0, root = kEmpty;
+      float ms = 0.0f;
+      cudaError_t e = lbvh_build(boxes.data(), (uint32_t)boxes.size(), sub, order, &root, rb, &depth, &ms);
+      if (e != cudaSuccess) return fail(NRB_ERR_CUDA, std::string("lbvh_build: ") + cudaGetErrorString(e));
+      H.gpu_build_ms += ms;
+      const int node_off = (int)bb.nodes.size();
+      const uint32_t tri_off = (uint32_t)bb.tri_order.size();
+      auto shift = [&](int c) -> int {
+        if (c >= 0) return c + node_off;
+        uint32_t lc = (uint32_t)~c;
+        return ~(int)((((lc >> 3) + tri_off) << 3) | (lc & 7u));
+      };
+      for (BvhNode nd : sub) {
+        nd.n3.x = shift(nd.n3.x);
+        nd.n3.y = shift(nd.n3.y);
+        bb.nodes.push_back(nd);
+      }
+      for (uint32_t pos : order) bb.tri_order.push_back((uint32_t)items[pos].payload);
+      *code = shift(root);
+      bb.max_depth_seen = std::max(bb.max_depth_seen, depth + 1);
+      return NRB_OK;
+    }
+    *code = bb.build_triangles(items, rb);
+    return NRB_OK;
+  };
   {
     std::vector<BuildItem> items;
     for (uint32_t i = 0; i < d.n_nodes; ++i) {
@@ -374,7 +409,9 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H) {
     }
     if (!items.empty()) {
       Box rb;
-      int code = bb.build_triangles(items, &rb);
+      int code = kEmpty;
+      int brc = build_set(items, &rb, &code);
+      if (brc) return brc;
       opaque_items.push_back(BuildItem{rb, code});
     }
   }
@@ -389,7 +426,9 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H) {
       for (uint64_t t = 0; t < n.tri_count; ++t) items.push_back(BuildItem{tri_box[node_tri_begin[i] + t], (int)(node_tri_begin[i] + t)});
       Box rb;
       bb.max_depth_seen = 0;
-      int code = bb.build_triangles(items, &rb);
+      int code = kEmpty;
+      int brc = build_set(items, &rb, &code);
+      if (brc) return brc;
       depth_tri = std::max(depth_tri, bb.max_depth_seen);
       Candidate c{};
       for (int k = 0; k < 3; ++k) c.lo[k] = rb.lo[k], c.hi[k] = rb.hi[k];
@@ -922,7 +961,14 @@ int nrb_device_count(void) {
 }
 
 int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out) {
+  return nrb_scene_create_opts(desc, device, nullptr, out);
+}
+
+int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOptions *opts, NrbScene **out) {
   if (!desc || !out) return fail(NRB_ERR_INVALID_ARG, "desc/out is NULL");
+  uint32_t builder = opts ? opts->builder : NRB_BUILDER_SAH;
+  if (const char *e = getenv("NRB_BUILDER")) builder = (std::string(e) == "lbvh") ? NRB_BUILDER_LBVH : NRB_BUILDER_SAH;
+  if (builder != NRB_BUILDER_SAH && builder != NRB_BUILDER_LBVH) return fail(NRB_ERR_INVALID_ARG, "unknown builder");
   if (desc->struct_size != sizeof(NrbSceneDesc) || desc->abi_version != NRB_ABI_VERSION)
     return fail(NRB_ERR_INVALID_ARG, "NrbSceneDesc struct_size / abi_version mismatch");
   int ndev = nrb_device_count();
@@ -942,10 +988,24 @@ int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out) {
   CU(cudaHostAlloc((void **)&S->h_counters, sizeof(Counters), cudaHostAllocDefault));
   CU(S->d_counters.ensure(sizeof(Counters)));
   HostScene H;
-  int rc = flatten_scene(*desc, H);
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = flatten_scene(*desc, H, builder);
   if (rc) return rc;
+  if (getenv("NRB_CHECK_BVH")) {  // structural self-check of whatever builder ran (tests)
+    std::string why;
+    if (check_bvh(H, why)) return fail(NRB_ERR_CUDA + 100, "internal BVH invariant violated: " + why);
+  }
   rc = upload_scene(*desc, H, *S);
   if (rc) return rc;
+  S->build_info.bvh_nodes = H.nodes.size();
+  S->build_info.triangles = H.tris.size();
+  S->build_info.shapes = H.shapes.size();
+  S->build_info.planes = H.planes.size();
+  S->build_info.transparent_candidates = H.candidates.size();
+  S->build_info.max_depth = (uint32_t)(H.depth_tri + H.depth_mid + H.depth_top);
+  S->build_info.build_ms = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  S->build_info.gpu_build_ms = H.gpu_build_ms;
+  S->build_info.builder = builder;
   S->grid_trace = S->sm_count * trace_blocks_per_sm(S->has_shapes);
   S->grid_tail = S->sm_count * 4;
   S->grid_shade = S->sm_count * shade_blocks_per_sm(S->has_shapes);
@@ -954,6 +1014,12 @@ int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out) {
 }
 
 void nrb_scene_destroy(NrbScene *scene) { delete scene; }
+
+int nrb_scene_build_info(const NrbScene *scene, NrbBuildInfo *info) {
+  if (!scene || !info) return fail(NRB_ERR_INVALID_ARG, "scene/info is NULL");
+  *info = scene->build_info;
+  return NRB_OK;
+}
 
 int nrb_scene_validate(const NrbSceneDesc *desc, NrbBuildInfo *info) {
   if (!desc) return fail(NRB_ERR_INVALID_ARG, "desc is NULL");

@@ -477,12 +477,13 @@ class Image:
 class Scene:
     """Scene (src/scene.rs:21-25).  Scene.new flattens and uploads (BVH build happens in the library)."""
 
-    def __init__(self, nodes, lights, background=(1.0, 1.0, 1.0), device=0, upload=True):
+    def __init__(self, nodes, lights, background=(1.0, 1.0, 1.0), device=0, upload=True, builder="sah"):
         self.nodes = list(nodes)
         self._lights = list(lights)
         self.background = tuple(float(x) for x in background)
         self.flat = FlatScene(self.nodes, self._lights, self.background)
         self.device = device
+        self.builder = builder  # "sah" (host binned SAH, default) or "lbvh" (device build)
         self._handle = None
         if upload:
             self.upload()
@@ -494,8 +495,16 @@ class Scene:
 
         lib = _lib.load()
         h = C.c_void_p()
-        _lib.check(lib.nrb_scene_create(C.byref(self.flat.desc), int(self.device), C.byref(h)))
+        opts = A.NrbBuildOptions(A.NRB_BUILDER_LBVH if self.builder == "lbvh" else A.NRB_BUILDER_SAH)
+        _lib.check(lib.nrb_scene_create_opts(C.byref(self.flat.desc), int(self.device), C.byref(opts), C.byref(h)))
         self._handle = h
+
+    def build_info(self):
+        from . import _lib
+
+        info = A.NrbBuildInfo()
+        _lib.check(_lib.load().nrb_scene_build_info(self.handle, C.byref(info)))
+        return info
 
     def lights(self):
         return self._lights

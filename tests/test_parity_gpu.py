@@ -282,3 +282,41 @@ def test_mesh_scene_driver_paths(gpu):
         np.testing.assert_allclose(img, base, rtol=0, atol=3e-5, err_msg=str(env))
         assert st.as_dict()["rays_total"] == st0.as_dict()["rays_total"], env
     scene.close()
+
+
+def test_device_lbvh_build_renders_the_same_image(gpu):
+    """§8f-1: the GPU LBVH build (Morton sort + Karras tree + refit) is a different tree over the same
+    triangles: same pixels as the host SAH build, valid structure, built on the device."""
+    from nrays_b200.loader3d import load_scene
+
+    cfg = configs.CONFIGS["C3"]
+    with _Env(NRB_CHECK_BVH=1):
+        text, res = cfg["text"](), cfg["resolver"](target_tris=60000, lod=4)
+        lights, nodes, cams = __import__("nrays_b200.loader3d", fromlist=["parse"]).parse(text, res)
+        sah = Scene(nodes, lights, (1, 1, 1), builder="sah")
+        lbvh = Scene(nodes, lights, (1, 1, 1), builder="lbvh")
+    bi_s, bi_l = sah.build_info(), lbvh.build_info()
+    assert bi_s.builder == A.NRB_BUILDER_SAH and bi_l.builder == A.NRB_BUILDER_LBVH
+    assert bi_l.gpu_build_ms > 0 and bi_s.gpu_build_ms == 0
+    assert bi_l.triangles == bi_s.triangles == 60000 and bi_l.max_depth <= 60
+    w, h = 192, 108
+    proj = cams[0].projection((w, h))
+    a, sa = render(sah, (w, h), 2, 1.0, cams[0].eye, proj, seed=4, return_stats=True)
+    b, sb = render(lbvh, (w, h), 2, 1.0, cams[0].eye, proj, seed=4, return_stats=True)
+    # identical hits except exact ties (shared edges), so only a handful of pixels may move
+    d = np.abs(a.pixels - b.pixels).max(axis=1)
+    assert (d > 1e-4).mean() < 2e-3, float((d > 1e-4).mean())
+    assert abs(int(sa.rays_total) - int(sb.rays_total)) <= 1e-3 * sa.rays_total
+    sah.close()
+    lbvh.close()
+    # hair: thin, overlapping geometry and many duplicate Morton cells
+    scene, camd, _ = configs.build("C4", target_tris=160000)
+    hair_nodes, hair_lights = scene.nodes, scene.lights()
+    with _Env(NRB_CHECK_BVH=1):
+        lb = Scene(hair_nodes, hair_lights, (1, 1, 1), builder="lbvh")
+    proj = camd.projection((128, 72))
+    a = render(scene, (128, 72), 1, 0.0, camd.eye, proj)
+    b = render(lb, (128, 72), 1, 0.0, camd.eye, proj)
+    assert (np.abs(a.pixels - b.pixels).max(axis=1) > 1e-4).mean() < 2e-3
+    scene.close()
+    lb.close()
