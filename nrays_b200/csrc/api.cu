@@ -701,6 +701,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   const uint64_t mem_ceiling = env_size("NRB_QUEUE_BYTES", 64ull << 30);
   const uint32_t S_total = (uint32_t)S.view.shadow_samples;
   const uint64_t tail_threshold = env_size("NRB_TAIL_RAYS", 4u << 20);
+  const uint32_t tail_min_wave = (uint32_t)env_size("NRB_TAIL_MIN_WAVE", 2);
   uint64_t primary = 0;
 
   const size_t wc_len = (size_t)fp.max_depth + 3;
@@ -754,7 +755,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
         }
         if (known_prev == 0 || S.child_factor == 0) break;
         bound = known_prev * (uint64_t)S.child_factor;
-        if (k >= 2 && bound <= tail_threshold) {
+        if (k >= tail_min_wave && bound <= tail_threshold) {
           // ---- tail: every lane follows its own ray chain to the end (see tail_kernel) -----------
           if (pending_shadow >= 0) {
             rc = trace_span(false, no_queue, nullptr, &wc[pending_shadow]);
@@ -781,13 +782,14 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
               rc = trace_span(false, no_queue, nullptr, &wc[t]);  // the chains' shadow rays
               if (rc) return rc;
             }
-            // rays spilled by hits that spawned both children start the next tail launch
             CU(cudaMemcpyAsync(&S.h_wave_counts[wave_base + t], &wc[t].n_rays, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            wave_counts_used = std::max(wave_counts_used, wave_base + t + 1);
+            if (S.child_factor < 2) break;  // a hit never spawns both children: nothing can be spilled, no sync needed
+            // rays spilled by hits that spawned both children start the next tail launch
             CU(cudaMemcpyAsync(&S.h_wave_counts[wave_base + t + 1], &wc[t + 1].n_rays, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
-            wave_counts_used = std::max(wave_counts_used, wave_base + t + 1);
             uint32_t spilled = S.h_wave_counts[wave_base + t + 1];
-            if (spilled == 0 || S.child_factor < 2) break;
+            if (spilled == 0) break;
             bound = spilled;
           }
           break;

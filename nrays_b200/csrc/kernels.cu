@@ -11,6 +11,8 @@
 // The reference recursion `trace` is linear in its reflection / refraction children, so each ray
 // carries a scalar weight and every hit / miss / unoccluded light sample adds its weighted colour
 // straight into the pixel accumulator (SURVEY §7 "Hard parts").
+#include <cooperative_groups.h>
+
 #include "device_math.cuh"
 #include "kernels.h"
 
@@ -743,7 +745,11 @@ __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : 4) tail_kernel(S
         c_trunc += (s.trunc_refl ? 1u : 0u) + (s.trunc_refr ? 1u : 0u);
         if (s.emit_sh) {
           c_shadow += S;
-          uint32_t sbase = atomicAdd(&wc[0].n_shadow, S);
+          // lanes that reach this point together reserve their slots with ONE atomic (coalesced group)
+          cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
+          uint32_t sbase = 0;
+          if (g.thread_rank() == 0) sbase = atomicAdd(&wc[0].n_shadow, S * g.size());
+          sbase = g.shfl(sbase, 0) + S * g.thread_rank();
           emit_shadow_rays<HAS_SHAPES, true>(sc, fp, r, s, sq, sbase, ctr, accum);
         }
         if (s.want_refl && s.want_refr) {
