@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -256,8 +256,8 @@ def run_ours(args, rank, local_rank, world):
         sampler.start()
         time.sleep(0.15)
     ms_dev, stats_dev = timed(step_device, args.steps, 0)
-    clocks = sampler.stop() if rank == 0 else None
     ms_e2e, stats_e2e = timed(step_e2e, args.steps, 0)
+    clocks = sampler.stop() if rank == 0 else None   # sampled across both timed regions
 
     def reduce(ms, stats):
         rays = sum(s["rays_total"] for s, _ in stats)
