@@ -540,8 +540,35 @@ int check_bvh(const HostScene &H, std::string &why) {
   return 0;
 }
 
+// Device node format: box centres + half extents (see device_types.cuh).  The half extent is rounded
+// up so the device box contains the builder's [lo, hi] box.
+std::vector<BvhNode> to_centre_half(const std::vector<BvhNode> &in) {
+  std::vector<BvhNode> out(in.size());
+  for (size_t i = 0; i < in.size(); ++i) {
+    const BvhNode &n = in[i];
+    const float lo[2][3] = {{n.n0.x, n.n0.z, n.n2.x}, {n.n1.x, n.n1.z, n.n2.z}};
+    const float hi[2][3] = {{n.n0.y, n.n0.w, n.n2.y}, {n.n1.y, n.n1.w, n.n2.w}};
+    float c[2][3], h[2][3];
+    for (int b = 0; b < 2; ++b)
+      for (int k = 0; k < 3; ++k) {
+        float l = std::max(lo[b][k], -1.0e30f), u = std::min(hi[b][k], 1.0e30f);
+        float cc = 0.5f * l + 0.5f * u;
+        float hh = std::max(u - cc, cc - l);
+        hh = hh * 1.0000005f + std::fabs(cc) * 1.2e-7f + 1e-30f;  // covers the rounding of cc and of u - cc
+        c[b][k] = cc;
+        h[b][k] = hh;
+      }
+    BvhNode &o = out[i];
+    o.n0 = make_float4(c[0][0], c[0][1], c[0][2], c[1][0]);
+    o.n1 = make_float4(c[1][1], c[1][2], h[0][0], h[0][1]);
+    o.n2 = make_float4(h[0][2], h[1][0], h[1][1], h[1][2]);
+    o.n3 = n.n3;
+  }
+  return out;
+}
+
 int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
-  CU(upload(S.d_nodes, H.nodes));
+  CU(upload(S.d_nodes, to_centre_half(H.nodes)));
   CU(upload(S.d_tris, H.tris));
   CU(upload(S.d_tri_uvs, H.tri_uvs));
   CU(upload(S.d_shapes, H.shapes));
@@ -702,6 +729,13 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   const uint32_t S_total = (uint32_t)S.view.shadow_samples;
   const uint64_t tail_threshold = env_size("NRB_TAIL_RAYS", 4u << 20);
   const uint32_t tail_min_wave = (uint32_t)env_size("NRB_TAIL_MIN_WAVE", 2);
+  // Dynamic fetch of the trace kernel: a warp pauses to refill its idle lanes once fewer than this many lanes are
+  // still traversing (0 = only when all 32 are done).  Measured (profiles/README.md): on the coherent headline
+  // config every non-zero setting loses 8-25 % (the refill rounds cost more than the idle lanes), on the incoherent
+  // hairball 20 lanes for shadow rays gains ~7 %; the default keeps whole packets.
+  const int refill_primary = (int)env_size("NRB_REFILL_PRIMARY", 0);
+  const int refill_rays = (int)env_size("NRB_REFILL_RAYS", 0);
+  const int refill_shadow = (int)env_size("NRB_REFILL_SHADOW", 0);
   uint64_t primary = 0;
 
   const size_t wc_len = (size_t)fp.max_depth + 3;
@@ -737,7 +771,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
       cudaEvent_t e0 = get_event(S, ev_used), e1 = get_event(S, ev_used);
       CU(cudaEventRecord(e0, st));
       launch_trace(S.view, S.has_shapes, fp, primary, q, S.d_hits.as<float4>(), wcc, slot_lo, n_slots, sq, accum, wcs,
-                   S.grid_trace, st);
+                   primary ? refill_primary : refill_rays, refill_shadow, S.grid_trace, st);
       CU(cudaEventRecord(e1, st));
       trace_spans.emplace_back(e0, e1);
       ++launches;
@@ -757,31 +791,36 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
         bound = known_prev * (uint64_t)S.child_factor;
         if (k >= tail_min_wave && bound <= tail_threshold) {
           // ---- tail: every lane follows its own ray chain to the end (see tail_kernel) -----------
-          if (pending_shadow >= 0) {
-            rc = trace_span(false, no_queue, nullptr, &wc[pending_shadow]);
-            if (rc) return rc;
-            pending_shadow = -1;
-          }
+          // The chains append their shadow rays behind the ones the last shade left untraced (same queue,
+          // same counter); ONE shadow launch per tail launch traces them all.
           for (uint32_t t = k; t < fp.max_depth; ++t) {
             const int tc = (int)(t & 1u);
             if (wave_base + t + 1 >= S.h_wave_cap) return fail(NRB_ERR_INVALID_ARG, "max_depth too large for the wave-count buffer");
             CU(ensure_ray_queue(S, 1 - tc, (uint32_t)std::max<uint64_t>(bound * 4, 4096)));  // spill queue
             if (S_total && S.sq_cap < 65536) {
+              if (pending_shadow >= 0) {  // the buffer is about to move: trace what it holds first
+                rc = trace_span(false, no_queue, nullptr, &wc[pending_shadow]);
+                if (rc) return rc;
+                pending_shadow = -1;
+              }
               CU(cudaStreamSynchronize(st));
               for (int c = 0; c < 3; ++c) CU(S.d_sq[c].ensure((size_t)65536 * 16));
               S.sq_cap = 65536;
             }
+            const int sh_wave = pending_shadow >= 0 ? pending_shadow : (int)t;  // counter the chains' shadow rays go to
             ShadowQueue sq{S.d_sq[0].as<float4>(), S.d_sq[1].as<float4>(), S.d_sq[2].as<float4>(), S.sq_cap};
             cudaEvent_t e0 = get_event(S, ev_used), e1 = get_event(S, ev_used);
             CU(cudaEventRecord(e0, st));
-            launch_tail(S.view, S.has_shapes, fp, ray_queue(S, tc), &wc[t], ray_queue(S, 1 - tc), sq, dc, accum, S.grid_tail, st);
+            launch_tail(S.view, S.has_shapes, fp, ray_queue(S, tc), &wc[t], ray_queue(S, 1 - tc), sq, dc, accum, &wc[sh_wave],
+                        S.grid_tail, st);
             CU(cudaEventRecord(e1, st));
             trace_spans.emplace_back(e0, e1);
             ++launches;
             if (S_total) {
-              rc = trace_span(false, no_queue, nullptr, &wc[t]);  // the chains' shadow rays
+              rc = trace_span(false, no_queue, nullptr, &wc[sh_wave]);  // pending shadow rays + the chains' shadow rays
               if (rc) return rc;
             }
+            pending_shadow = -1;
             CU(cudaMemcpyAsync(&S.h_wave_counts[wave_base + t], &wc[t].n_rays, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             wave_counts_used = std::max(wave_counts_used, wave_base + t + 1);
             if (S.child_factor < 2) break;  // a hit never spawns both children: nothing can be spilled, no sync needed
@@ -1034,6 +1073,15 @@ int nrb_scene_validate(const NrbSceneDesc *desc, NrbBuildInfo *info) {
   double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   std::string why;
   if (check_bvh(H, why)) return fail(NRB_ERR_CUDA + 100, "internal BVH invariant violated: " + why);
+  if (const char *path = getenv("NRB_DUMP_BVH")) {  // builder experiments (scripts/bvh_sim.cpp): nodes + triangles as built
+    if (FILE *f = fopen(path, "wb")) {
+      uint64_t hdr[4] = {H.nodes.size(), H.tris.size(), (uint64_t)(uint32_t)H.root_all, (uint64_t)(uint32_t)H.root_opaque};
+      fwrite(hdr, sizeof(hdr), 1, f);
+      fwrite(H.nodes.data(), sizeof(BvhNode), H.nodes.size(), f);
+      fwrite(H.tris.data(), sizeof(Tri), H.tris.size(), f);
+      fclose(f);
+    }
+  }
   if (info) {
     std::memset(info, 0, sizeof(*info));
     info->bvh_nodes = H.nodes.size();

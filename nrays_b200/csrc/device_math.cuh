@@ -413,6 +413,30 @@ NRB_DI bool cast_tri(V3 v0, V3 e1, V3 e2, V3 o, V3 d, float tlimit, float &toi, 
   return true;
 }
 
+// Same test with the comparison chosen at run time (the persistent trace loop mixes any-hit and closest-hit lanes).
+NRB_DI bool cast_tri_rt(V3 v0, V3 e1, V3 e2, V3 o, V3 d, float tlimit, bool inclusive, float &toi, float &bv, float &bw) {
+  V3 n = cross(e1, e2);
+  float dd = dot(n, d);
+  V3 ap = o - v0;
+  float t = dot(ap, n);
+  if (dd == 0.0f) return false;
+  if ((t < 0.0f && dd < 0.0f) || (t > 0.0f && dd > 0.0f)) return false;
+  float D = fabsf(dd);
+  float at = fabsf(t);
+  float lim = tlimit * D;
+  if (inclusive ? !(at <= lim) : !(at < lim)) return false;
+  V3 e = cross(ap, d);  // = -(d x ap)
+  float s = t < 0.0f ? -1.0f : 1.0f;
+  float v = s * dot(e2, e);
+  float w = -s * dot(e1, e);
+  if (v < 0.0f || v > D || w < 0.0f || v + w > D) return false;
+  float invd = 1.0f / D;
+  toi = at * invd;
+  bv = v * invd;
+  bw = w * invd;
+  return true;
+}
+
 // ---- Texture2d::sample — src/texture2d.rs:207-256 -----------------------------------------------
 NRB_DI float4 tex_at(const SceneView &sc, const Texture &t, uint32_t x, uint32_t y) {
   uint32_t i = y * t.w + x;

@@ -9,12 +9,16 @@
 namespace nrb {
 
 // ---- BVH ------------------------------------------------------------------------------------
-// One 64-byte node holds BOTH children's boxes (Aila-Laine layout), so one traversal step is four
-// 16-byte loads of one cache-line-aligned record and tests two boxes.
+// One 64-byte node holds BOTH children's boxes (Aila-Laine layout), so one traversal step fetches one
+// cache-line-aligned record (two 256-bit loads) and tests two boxes.
+// The builders (bvh_build.cpp, lbvh.cu) and the host-side checks use the lo/hi form:
 //   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
 //   n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
 //   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
 //   n3 = (child0, child1, -, -) as int bits
+// The DEVICE copy is converted at upload (api.cu: to_centre_half) to centres + half extents, which turns
+// the slab test into 9 FFMA + 4 min/max per box (kernels.cu: test_children):
+//   n0 = (c0.centre.xyz, c1.centre.x)   n1 = (c1.centre.yz, c0.half.xy)   n2 = (c0.half.z, c1.half.xyz)   n3 as above
 // Child code c:  c >= 0 -> inner node index;  c < 0 -> leaf, ~c = (first << 3) | ((count-1) << 1) | is_shape
 //   is_shape = 0: triangles [first, first+count) of the leaf-ordered triangle array (count <= 4)
 //   is_shape = 1: analytic shape `first` of the shape table (count == 1)

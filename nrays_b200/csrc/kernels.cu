@@ -93,6 +93,69 @@ struct Hit {
   float u, v;
 };
 
+// One 64-byte node record (device_types.cuh): centres + half extents of both children, child codes.
+struct NodeRec {
+  float4 n0, n1, n2;
+  int c0, c1;
+};
+
+NRB_DI NodeRec load_node(const SceneView &sc, int node) {
+  NodeRec r;
+  const BvhNode *np = sc.nodes + node;
+#if NRB_NODE_LOADS == 1
+  // two 256-bit loads (LDG.E.256, sm_100+) fetch the whole record; the child codes arrive with the boxes
+  int pad0, pad1;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.n0.x), "=f"(r.n0.y), "=f"(r.n0.z), "=f"(r.n0.w), "=f"(r.n1.x), "=f"(r.n1.y), "=f"(r.n1.z), "=f"(r.n1.w)
+               : "l"(np));
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.n2.x), "=f"(r.n2.y), "=f"(r.n2.z), "=f"(r.n2.w), "=r"(r.c0), "=r"(r.c1), "=r"(pad0), "=r"(pad1)
+               : "l"(reinterpret_cast<const char *>(np) + 32));
+#elif NRB_NODE_LOADS == 2
+  // 256 + 128 + 64 bits: only the 56 bytes in use cross the L1 data pipe
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.n0.x), "=f"(r.n0.y), "=f"(r.n0.z), "=f"(r.n0.w), "=f"(r.n1.x), "=f"(r.n1.y), "=f"(r.n1.z), "=f"(r.n1.w)
+               : "l"(np));
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.n2.x), "=f"(r.n2.y), "=f"(r.n2.z), "=f"(r.n2.w)
+               : "l"(reinterpret_cast<const char *>(np) + 32));
+  asm volatile("ld.global.nc.v2.b32 {%0,%1}, [%2];" : "=r"(r.c0), "=r"(r.c1) : "l"(reinterpret_cast<const char *>(np) + 48));
+#else
+  const float4 *fp4 = reinterpret_cast<const float4 *>(np);
+  r.n0 = __ldg(fp4), r.n1 = __ldg(fp4 + 1), r.n2 = __ldg(fp4 + 2);
+  int2 ch = __ldg(reinterpret_cast<const int2 *>(fp4 + 3));
+  r.c0 = ch.x, r.c1 = ch.y;
+#endif
+  return r;
+}
+
+// Per-ray constants of the slab test: t(plane) = plane * (1/d) - o * (1/d).
+struct RayPre {
+  float idx, idy, idz, oodx, oody, oodz;
+};
+NRB_DI RayPre ray_pre(V3 o, V3 d) {
+  const float ooeps = 1.0e-24f;
+  RayPre p;
+  p.idx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+  p.idy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+  p.idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+  p.oodx = o.x * p.idx, p.oody = o.y * p.idy, p.oodz = o.z * p.idz;
+  return p;
+}
+
+// Both children's slab tests in centre / half-extent form: t(centre) -+ half * |1/d| — 9 FFMA + 4
+// min/max per box and no lo/hi sort (the FMNMX pipe, not the FMA pipe, limits the classic form).
+NRB_DI void test_children(const NodeRec &n, const RayPre &p, float tbest, float &c0min, float &c0max, float &c1min,
+                          float &c1max) {
+  const float aidx = fabsf(p.idx), aidy = fabsf(p.idy), aidz = fabsf(p.idz);
+  float c0tx = fmaf(n.n0.x, p.idx, -p.oodx), c0ty = fmaf(n.n0.y, p.idy, -p.oody), c0tz = fmaf(n.n0.z, p.idz, -p.oodz);
+  float c1tx = fmaf(n.n0.w, p.idx, -p.oodx), c1ty = fmaf(n.n1.x, p.idy, -p.oody), c1tz = fmaf(n.n1.y, p.idz, -p.oodz);
+  c0min = fmaxf(fmaxf(fmaf(-n.n1.z, aidx, c0tx), fmaf(-n.n1.w, aidy, c0ty)), fmaxf(fmaf(-n.n2.x, aidz, c0tz), 0.0f));
+  c0max = fminf(fminf(fmaf(n.n1.z, aidx, c0tx), fmaf(n.n1.w, aidy, c0ty)), fminf(fmaf(n.n2.x, aidz, c0tz), tbest));
+  c1min = fmaxf(fmaxf(fmaf(-n.n2.y, aidx, c1tx), fmaf(-n.n2.z, aidy, c1ty)), fmaxf(fmaf(-n.n2.w, aidz, c1tz), 0.0f));
+  c1max = fminf(fminf(fmaf(n.n2.y, aidx, c1tx), fmaf(n.n2.z, aidy, c1ty)), fminf(fmaf(n.n2.w, aidz, c1tz), tbest));
+}
+
 // ANY = true: return at the first hit with toi <= tmax (shadow rays vs opaque geometry).
 // ANY = false: closest hit with toi < tmax (strict, best_first_search keeps the first of equals).
 template <bool HAS_SHAPES, bool ANY>
@@ -102,11 +165,7 @@ NRB_DI bool traverse(const SceneView &sc, int root, V3 o, V3 d, float tmax, Hit 
   stack[0] = kEmpty;
   int node = root;
   bool found = false;
-  const float ooeps = 1.0e-24f;
-  float idx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
-  float idy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
-  float idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
-  float oodx = o.x * idx, oody = o.y * idy, oodz = o.z * idz;
+  const RayPre pre = ray_pre(o, d);
   float tbest = tmax;
 #ifdef NRB_COUNT_VISITS
   unsigned dbg_n = 0, dbg_t = 0;
@@ -118,29 +177,19 @@ NRB_DI bool traverse(const SceneView &sc, int root, V3 o, V3 d, float tmax, Hit 
 #ifdef NRB_COUNT_VISITS
       ++dbg_n;
 #endif
-      const float4 *np = reinterpret_cast<const float4 *>(sc.nodes + node);
-      float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
-      int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
-      float c0lox = fmaf(n0.x, idx, -oodx), c0hix = fmaf(n0.y, idx, -oodx);
-      float c0loy = fmaf(n0.z, idy, -oody), c0hiy = fmaf(n0.w, idy, -oody);
-      float c0loz = fmaf(n2.x, idz, -oodz), c0hiz = fmaf(n2.y, idz, -oodz);
-      float c1lox = fmaf(n1.x, idx, -oodx), c1hix = fmaf(n1.y, idx, -oodx);
-      float c1loy = fmaf(n1.z, idy, -oody), c1hiy = fmaf(n1.w, idy, -oody);
-      float c1loz = fmaf(n2.z, idz, -oodz), c1hiz = fmaf(n2.w, idz, -oodz);
-      float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
-      float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tbest));
-      float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
-      float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tbest));
+      const NodeRec n = load_node(sc, node);
+      float c0min, c0max, c1min, c1max;
+      test_children(n, pre, tbest, c0min, c0max, c1min, c1max);
       bool h0 = c0max >= c0min, h1 = c1max >= c1min;
       if (!h0 && !h1) {
         node = stack[sp--];
       } else {
-        node = h0 ? ch.x : ch.y;
+        node = h0 ? n.c0 : n.c1;
         if (h0 && h1) {
-          int far = ch.y;
-          if (c1min < c0min) {
-            far = ch.x;
-            node = ch.y;
+          int far = n.c1;
+          if (!ANY && c1min < c0min) {  // any-hit needs no front-to-back order
+            far = n.c0;
+            node = n.c1;
           }
           stack[++sp] = far;
         }
@@ -184,6 +233,143 @@ NRB_DI bool traverse(const SceneView &sc, int root, V3 o, V3 d, float tmax, Hit 
   atomicMax(&g_dbg[3], (unsigned long long)(dbg_n + dbg_t));
 #endif
   return found;
+}
+
+// Resumable form of the same loop for the persistent trace kernel.  The lane's traversal state lives in
+// `LaneTrav` (+ its stack) across calls; trav_run() advances it until this lane's traversal is complete
+// (s.node == kEmpty) OR the number of lanes still traversing drops below `min_active` — then every lane
+// returns so the warp can hand new rays to its idle lanes (persistent threads with dynamic fetch: the
+// "active-ray compaction" of the north star).  `any` is a per-lane run-time flag here: shadow rays run
+// any-hit under root_opaque and closest-hit under a transparent candidate's sub-root.
+//
+// Register budget: the node loop needs only (1/d, o/d, tbest, node, sp).  Everything touched per LEAF or per
+// RAY — origin, direction, the best hit's (prim, u, v) — is parked in the lane's local-memory block in front
+// of the traversal stack (slots kLm*), because the compiler would otherwise spill the loop's own operands.
+struct LaneTrav {
+  RayPre pre;
+  int node, sp;
+  float tbest;  // any: tmax (inclusive); closest: current best toi (exclusive)
+};
+constexpr int kLmO = 0, kLmD = 3, kLmPrim = 6, kLmU = 7, kLmV = 8, kLmSentinel = 9;  // then the stack proper
+constexpr int kLmSize = kLmSentinel + 1 + kStackSize;
+
+NRB_DI V3 lm_vec(const int *lm, int at) {
+  return mk(__int_as_float(lm[at]), __int_as_float(lm[at + 1]), __int_as_float(lm[at + 2]));
+}
+NRB_DI void lm_set_ray(int *lm, V3 o, V3 d) {
+  lm[kLmO] = __float_as_int(o.x), lm[kLmO + 1] = __float_as_int(o.y), lm[kLmO + 2] = __float_as_int(o.z);
+  lm[kLmD] = __float_as_int(d.x), lm[kLmD + 1] = __float_as_int(d.y), lm[kLmD + 2] = __float_as_int(d.z);
+}
+NRB_DI void lm_set_hit(int *lm, uint32_t prim, float u, float v) {
+  lm[kLmPrim] = (int)prim, lm[kLmU] = __float_as_int(u), lm[kLmV] = __float_as_int(v);
+}
+
+NRB_DI void trav_start(LaneTrav &s, int *lm, int root, float tlimit) {
+  lm[kLmSentinel] = kEmpty;
+  lm[kLmPrim] = (int)kMiss;
+  s.sp = kLmSentinel;
+  s.node = root;
+  s.tbest = tlimit;
+}
+
+template <bool HAS_SHAPES>
+NRB_DI void trav_run(const SceneView &sc, LaneTrav &s, int *lm, bool any, int min_active) {
+  int node = s.node, sp = s.sp;
+  float tbest = s.tbest;
+  while (node != kEmpty) {
+    while ((unsigned)node < (unsigned)kEmpty) {
+      const NodeRec n = load_node(sc, node);
+      float c0min, c0max, c1min, c1max;
+      test_children(n, s.pre, tbest, c0min, c0max, c1min, c1max);
+      bool h0 = c0max >= c0min, h1 = c1max >= c1min;
+      if (!h0 && !h1) {
+        node = lm[sp--];
+      } else {
+        node = h0 ? n.c0 : n.c1;
+        if (h0 && h1) {
+          int far = n.c1;
+          if (c1min < c0min) {
+            far = n.c0;
+            node = n.c1;
+          }
+          lm[++sp] = far;
+        }
+      }
+    }
+    while (node < 0) {
+      uint32_t code = (uint32_t)~node;
+      uint32_t first = code >> 3, cnt = ((code >> 1) & 3u) + 1u;
+      bool hit_any = false;
+      const V3 o = lm_vec(lm, kLmO), d = lm_vec(lm, kLmD);
+      if (HAS_SHAPES && (code & 1u)) {
+        Inter it;
+        if (cast_shape(sc.shapes[first], o, d, it) && (any ? it.toi <= tbest : it.toi < tbest)) {
+          tbest = it.toi;
+          lm_set_hit(lm, kShapeBit | first, it.u, it.v);
+          hit_any = any;
+        }
+      } else {
+        const float4 *tp = reinterpret_cast<const float4 *>(sc.tris + first);
+        for (uint32_t k = 0; k < cnt && !hit_any; ++k) {
+          float4 t0 = __ldg(tp + 3 * k), t1 = __ldg(tp + 3 * k + 1), t2 = __ldg(tp + 3 * k + 2);
+          float toi, bv, bw;
+          if (cast_tri_rt(mk(t0.x, t0.y, t0.z), mk(t1.x, t1.y, t1.z), mk(t2.x, t2.y, t2.z), o, d, tbest, any, toi, bv, bw)) {
+            tbest = toi;
+            lm_set_hit(lm, first + k, bv, bw);
+            hit_any = any;
+          }
+        }
+      }
+      node = hit_any ? kEmpty : lm[sp--];
+    }
+    if (__popc(__activemask()) < min_active) break;  // dynamic fetch: let the warp refill its idle lanes
+  }
+  s.node = node, s.sp = sp, s.tbest = tbest;
+}
+
+// Hands queue entries to the idle lanes of a persistent warp.  The warp keeps a private pool
+// [pool_base, pool_base + pool_left) of entries taken from the global cursor 32 * kFetchPackets at a time
+// (one atomic per chunk); idle lanes get consecutive indices.
+struct RayPool {  // one per warp, in shared memory (keeps three registers out of the traversal loop)
+  uint32_t base, left, more;  // more: the global cursor may still have entries
+};
+constexpr uint32_t kNoRay = 0xFFFFFFFFu;
+
+NRB_DI void pool_reset(RayPool *pool) {
+  __syncwarp();
+  if (lane_id() == 0) pool->base = 0u, pool->left = 0u, pool->more = 1u;
+  __syncwarp();
+}
+
+NRB_DI bool pool_empty(const RayPool *pool) { return pool->more == 0u && pool->left == 0u; }
+
+NRB_DI uint32_t pool_assign(RayPool *pool, bool idle, uint32_t *cursor, uint32_t count) {
+  const uint32_t lane = lane_id();
+  const uint32_t mask = __ballot_sync(0xFFFFFFFFu, idle);
+  uint32_t mine = kNoRay;
+  if (mask == 0u) return mine;
+  uint32_t base = pool->base, left = pool->left, more = pool->more;
+  __syncwarp();
+  const uint32_t need = __popc(mask), rank = __popc(mask & ((1u << lane) - 1u));
+  uint32_t take = min(need, left);
+  if (idle && rank < take) mine = base + rank;
+  base += take, left -= take;
+  if (take < need && more) {
+    uint32_t nb = 0;
+    if (lane == 0) nb = atomicAdd(cursor, 32u * kFetchPackets);
+    nb = __shfl_sync(0xFFFFFFFFu, nb, 0);
+    if (nb >= count) {
+      more = 0u;
+    } else {
+      base = nb, left = min(32u * kFetchPackets, count - nb);
+      const uint32_t take2 = min(need - take, left);
+      if (idle && rank >= take && rank < take + take2) mine = base + (rank - take);
+      base += take2, left -= take2;
+    }
+  }
+  if (lane == 0) pool->base = base, pool->left = left, pool->more = more;
+  __syncwarp();
+  return mine;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -285,6 +471,36 @@ NRB_DI bool shadow_candidate(const SceneView &sc, int root, int node_id, V3 o, V
   return true;  // opaque
 }
 
+// The transparent-candidate part of the shadow query: every candidate SceneNode whose box the segment
+// crosses is resolved by its own closest hit (filter or occlusion).
+template <bool HAS_SHAPES>
+NRB_DI bool shadow_candidates(const SceneView &sc, V3 o, V3 d, float tmax, V3 &filter) {
+  bool occluded = false;
+  {
+    for (int c = 0; c < sc.n_candidates && !occluded; ++c) {
+      const Candidate cd = sc.candidates[c];
+      // slab test against the candidate's box (bv cost), origin-inside counts as hit
+      float t0 = 0.0f, t1 = tmax;
+      bool miss = false;
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        float oi = comp(o, ax), di = comp(d, ax);
+        if (di == 0.0f) {
+          if (oi < cd.lo[ax] || oi > cd.hi[ax]) miss = true;
+        } else {
+          float inv = 1.0f / di;
+          float ta = (cd.lo[ax] - oi) * inv, tb = (cd.hi[ax] - oi) * inv;
+          t0 = fmaxf(t0, fminf(ta, tb));
+          t1 = fminf(t1, fmaxf(ta, tb));
+        }
+      }
+      if (miss || t0 > t1) continue;
+      occluded = shadow_candidate<HAS_SHAPES>(sc, cd.root, cd.node, o, d, tmax, filter);
+    }
+  }
+  return occluded;
+}
+
 template <bool HAS_SHAPES>
 NRB_DI void shadow_query(const SceneView &sc, V3 o, V3 d, float tmax, uint32_t pix, V3 contrib, float4 *accum) {
   bool occluded = false;
@@ -319,9 +535,61 @@ NRB_DI void shadow_query(const SceneView &sc, V3 o, V3 d, float tmax, uint32_t p
     Hit h;
     occluded = traverse<HAS_SHAPES, true>(sc, sc.root_opaque, o, d, tmax, h);
   }
-  if (!occluded) {
-    for (int c = 0; c < sc.n_candidates && !occluded; ++c) {
-      const Candidate cd = sc.candidates[c];
+  if (!occluded) occluded = shadow_candidates<HAS_SHAPES>(sc, o, d, tmax, filter);
+  if (!occluded) accum_add(accum, pix, cmul(contrib, filter));
+}
+
+template <bool HAS_SHAPES>
+NRB_DI void shadow_ray(const SceneView &sc, const ShadowQueue &q, uint32_t i, float4 *accum) {
+  float4 a = q.a[i], b = q.b[i], c = q.c[i];
+  shadow_query<HAS_SHAPES>(sc, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), a.w, __float_as_uint(b.w), mk(c.x, c.y, c.z), accum);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The persistent trace kernel: ONE launch per wave drains the shadow queue of the previous wave
+// (any-hit + transparent filter, adds into the pixel accumulator) and the ray queue of this wave
+// (closest hit -> hit records).  Grid = SMs x resident CTAs.  Every lane owns one ray at a time; when
+// fewer than `min_active` lanes of a warp are still traversing, the warp pauses and refills its idle
+// lanes from the queue (pool_assign), so SIMD utilisation does not decay to the slowest ray of a packet.
+// Even CTAs start on the shadow queue, odd CTAs on the ray queue, then swap: in small (latency-bound)
+// waves both queues progress at once.  PRIMARY: wave 0 generates its rays from the sample slot instead
+// of reading a queue.
+// ---------------------------------------------------------------------------------------------
+
+// Shadow-ray state machine.  Phase -1: any-hit under root_opaque.  Phase c >= 0: closest hit
+// of transparent candidate c (its own sub-root), resolved through Material::ambiant.  Returns true if a
+// traversal was started, false if the ray is finished (occluded, or accumulated into its pixel).
+template <bool HAS_SHAPES>
+NRB_DI bool shadow_advance(const SceneView &sc, const ShadowQueue &sq, uint32_t idx, LaneTrav &s, int *lm, int &cand,
+                           bool first, float4 *accum) {
+  // The transparent filter is folded into the entry's contribution in place (the entry belongs to this lane),
+  // so the state carried across trav_run calls is just (idx, cand).
+  const uint32_t prim = (uint32_t)lm[kLmPrim];
+  if (first) {
+    cand = -1;
+    if (sc.root_opaque != kEmpty) {
+      trav_start(s, lm, sc.root_opaque, sq.a[idx].w);
+      return true;
+    }
+  } else if (cand < 0) {
+    if (prim != kMiss) return false;  // an opaque occluder
+  } else if (prim != kMiss) {
+    // closest hit of this candidate node within tmax: filter or occlude (src/scene.rs:313-337)
+    Surface sf;
+    reconstruct<HAS_SHAPES>(sc, lm_vec(lm, kLmO), lm_vec(lm, kLmD), prim, __int_as_float(lm[kLmU]), __int_as_float(lm[kLmV]), sf);
+    const NodeInfo ni = sc.node_info[sc.candidates[cand].node];
+    float4 c = mat_ambiant(sc, sc.materials[ni.material], sf);
+    float alpha = c.w * ni.alpha;
+    if (!(alpha < 1.0f)) return false;
+    float k = 1.0f - alpha;
+    float4 e = sq.c[idx];
+    sq.c[idx] = make_float4(e.x * c.x * k, e.y * c.y * k, e.z * c.z * k, e.w);
+  }
+  if (cand + 1 < sc.n_candidates) {
+    const float tmax = sq.a[idx].w;
+    const V3 o = lm_vec(lm, kLmO), d = lm_vec(lm, kLmD);
+    for (++cand; cand < sc.n_candidates; ++cand) {
+      const Candidate cd = sc.candidates[cand];
       // slab test against the candidate's box (bv cost), origin-inside counts as hit
       float t0 = 0.0f, t1 = tmax;
       bool miss = false;
@@ -338,91 +606,145 @@ NRB_DI void shadow_query(const SceneView &sc, V3 o, V3 d, float tmax, uint32_t p
         }
       }
       if (miss || t0 > t1) continue;
-      occluded = shadow_candidate<HAS_SHAPES>(sc, cd.root, cd.node, o, d, tmax, filter);
+      trav_start(s, lm, cd.root, nextafterf(tmax, 3.402823466e+38f));  // closest hit with toi <= tmax
+      return true;
     }
   }
-  if (!occluded) accum_add(accum, pix, cmul(contrib, filter));
+  const float4 b = sq.b[idx], c = sq.c[idx];
+  accum_add(accum, __float_as_uint(b.w), mk(c.x, c.y, c.z));
+  return false;
+}
+
+// Planes of the shadow query (always tested).  Returns true if the ray is occluded.
+NRB_DI bool shadow_planes(const SceneView &sc, const ShadowQueue &sq, uint32_t idx, V3 o, V3 d, float tmax) {
+  for (int p = 0; p < sc.n_planes; ++p) {
+    const Shape &sh = sc.shapes[sc.planes[p]];
+    Inter it;
+    if (!(cast_shape(sh, o, d, it) && it.toi <= tmax)) continue;
+    const NodeInfo ni = sc.node_info[sh.node];
+    if (!(ni.flags & 1)) return true;
+    // transparent candidate plane: its (only) hit filters or occludes
+    Surface sf;
+    sf.n = it.n, sf.u = it.u, sf.v = it.v, sf.has_uv = it.has_uv, sf.node = sh.node;
+    float4 c = mat_ambiant(sc, sc.materials[ni.material], sf);
+    float alpha = c.w * ni.alpha;
+    if (!(alpha < 1.0f)) return true;
+    float k = 1.0f - alpha;
+    float4 e = sq.c[idx];
+    sq.c[idx] = make_float4(e.x * c.x * k, e.y * c.y * k, e.z * c.z * k, e.w);
+  }
+  return false;
 }
 
 template <bool HAS_SHAPES>
-NRB_DI void shadow_ray(const SceneView &sc, const ShadowQueue &q, uint32_t i, float4 *accum) {
-  float4 a = q.a[i], b = q.b[i], c = q.c[i];
-  shadow_query<HAS_SHAPES>(sc, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), a.w, __float_as_uint(b.w), mk(c.x, c.y, c.z), accum);
-}
-
-// ---------------------------------------------------------------------------------------------
-// The persistent trace kernel: ONE launch per wave drains the shadow queue of the previous wave
-// (any-hit + transparent filter, adds into the pixel accumulator) and then the ray queue of this
-// wave (closest hit -> hit records).  Grid = SMs x resident CTAs; each warp pulls packets of
-// kFetchPackets x 32 rays with one atomic on a per-wave cursor.  PRIMARY: wave 0 generates its rays
-// from the sample slot instead of reading a queue.
-// ---------------------------------------------------------------------------------------------
-template <bool HAS_SHAPES>
-NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *accum, WaveCounters *wc_shadow) {
-  const uint32_t lane = lane_id();
+NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *accum, WaveCounters *wc_shadow, int min_active,
+                         RayPool *pool, int *lm) {
   const uint32_t count = min(wc_shadow->n_shadow, sq.capacity);
+  LaneTrav s;
+  s.node = kEmpty;
+  pool_reset(pool);
+  bool active = false;
+  uint32_t idx = 0;
+  int cand = -1;
   while (true) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&wc_shadow->fetch_shadow, 32u * kFetchPackets);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= count) break;
-#pragma unroll 1
-    for (int pk = 0; pk < kFetchPackets; ++pk) {
-      uint32_t i = base + 32u * pk + lane;
-      if (i < count) shadow_ray<HAS_SHAPES>(sc, sq, i, accum);
+    const uint32_t mine = pool_assign(pool, !active, &wc_shadow->fetch_shadow, count);
+    if (mine != kNoRay) {
+      idx = mine;
+      const float4 a = sq.a[idx], b = sq.b[idx];
+      const V3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
+      lm_set_ray(lm, o, d);
+      s.pre = ray_pre(o, d);
+      bool occluded = false;
+      if (HAS_SHAPES) occluded = shadow_planes(sc, sq, idx, o, d, a.w);
+      active = !occluded && shadow_advance<HAS_SHAPES>(sc, sq, idx, s, lm, cand, true, accum);
+    }
+    if (__ballot_sync(0xFFFFFFFFu, active) == 0u) {
+      if (pool_empty(pool)) break;
+      continue;
+    }
+    if (active) {
+      trav_run<HAS_SHAPES>(sc, s, lm, cand < 0, min_active);
+      if (s.node == kEmpty) active = shadow_advance<HAS_SHAPES>(sc, sq, idx, s, lm, cand, false, accum);
     }
   }
 }
 
 template <bool HAS_SHAPES, bool PRIMARY>
 NRB_DI void drain_closest(const SceneView &sc, const FrameParams &fp, const RayQueue &q, float4 *hits,
-                          WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots) {
-  const uint32_t lane = lane_id();
+                          WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, int min_active, RayPool *pool,
+                          int *lm) {
   const uint32_t count = PRIMARY ? n_slots : wc_closest->n_rays;
+  LaneTrav s;
+  s.node = kEmpty;
+  pool_reset(pool);
+  bool active = false;
+  uint32_t idx = 0;
   while (true) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&wc_closest->fetch_closest, 32u * kFetchPackets);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= count) break;
-#pragma unroll 1
-    for (int pk = 0; pk < kFetchPackets; ++pk) {
-      uint32_t i = base + 32u * pk + lane;
-      if (i < count) {
-        V3 o, d;
-        bool valid = true;
-        if (PRIMARY) {
-          uint32_t gid;
-          valid = primary_ray(fp, slot_lo + i, o, d, gid);
-        } else {
-          float4 a = q.a[i], b = q.b[i];
-          o = mk(a.x, a.y, a.z), d = mk(a.w, b.x, b.y);
-        }
+    const uint32_t mine = pool_assign(pool, !active, &wc_closest->fetch_closest, count);
+    if (mine != kNoRay) {
+      idx = mine;
+      bool valid = true;
+      V3 o, d;
+      if (PRIMARY) {
+        uint32_t gid;
+        valid = primary_ray(fp, slot_lo + idx, o, d, gid);
+      } else {
+        const float4 a = q.a[idx], b = q.b[idx];
+        o = mk(a.x, a.y, a.z), d = mk(a.w, b.x, b.y);
+      }
+      if (!valid) {
         // slots outside the image (ragged tiles) are marked so shade skips them
-        hits[i] = valid ? closest_hit<HAS_SHAPES>(sc, o, d) : make_float4(0.0f, __uint_as_float(kSkip), 0.0f, 0.0f);
+        hits[idx] = make_float4(0.0f, __uint_as_float(kSkip), 0.0f, 0.0f);
+      } else {
+        lm_set_ray(lm, o, d);
+        s.pre = ray_pre(o, d);
+        trav_start(s, lm, sc.root_all, 3.402823466e+38f);
+        if (HAS_SHAPES) {
+          // planes have infinite AABBs: always tested, never in the BVH
+          for (int p = 0; p < sc.n_planes; ++p) {
+            int si = sc.planes[p];
+            Inter it;
+            if (cast_shape(sc.shapes[si], o, d, it) && it.toi < s.tbest) {
+              s.tbest = it.toi;
+              lm_set_hit(lm, kShapeBit | (uint32_t)si, 0.0f, 0.0f);
+            }
+          }
+        }
+        active = true;
+      }
+    }
+    if (__ballot_sync(0xFFFFFFFFu, active) == 0u) {
+      if (pool_empty(pool)) break;
+      continue;
+    }
+    if (active) {
+      trav_run<HAS_SHAPES>(sc, s, lm, false, min_active);
+      if (s.node == kEmpty) {
+        const uint32_t prim = (uint32_t)lm[kLmPrim];
+        const bool hit = prim != kMiss;
+        hits[idx] = make_float4(s.tbest, __uint_as_float(prim), hit ? __int_as_float(lm[kLmU]) : 0.0f,
+                                hit ? __int_as_float(lm[kLmV]) : 0.0f);
+        active = false;
       }
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// The persistent trace kernel: ONE launch per wave drains the shadow queue of the previous wave
-// (any-hit + transparent filter, adds into the pixel accumulator) and the ray queue of this wave
-// (closest hit -> hit records).  Grid = SMs x resident CTAs; each warp pulls packets of
-// kFetchPackets x 32 rays with one atomic on a per-wave cursor.  Even CTAs start on the shadow queue,
-// odd CTAs on the ray queue, then swap: in small (latency-bound) waves both queues progress at once.
-// PRIMARY: wave 0 generates its rays from the sample slot instead of reading a queue.
-// ---------------------------------------------------------------------------------------------
 template <bool HAS_SHAPES, bool PRIMARY>
-__global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 6 : kTraceMinBlocks) trace_kernel(SceneView sc, FrameParams fp, RayQueue q, float4 *hits,
-                                                           WaveCounters *wc_closest, uint32_t slot_lo,
-                                                           uint32_t n_slots, ShadowQueue sq, float4 *accum,
-                                                           WaveCounters *wc_shadow) {
-  if (blockIdx.x & 1u) {
-    if (wc_closest) drain_closest<HAS_SHAPES, PRIMARY>(sc, fp, q, hits, wc_closest, slot_lo, n_slots);
-    if (wc_shadow) drain_shadow<HAS_SHAPES>(sc, sq, accum, wc_shadow);
-  } else {
-    if (wc_shadow) drain_shadow<HAS_SHAPES>(sc, sq, accum, wc_shadow);
-    if (wc_closest) drain_closest<HAS_SHAPES, PRIMARY>(sc, fp, q, hits, wc_closest, slot_lo, n_slots);
+__global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 6 : kTraceMinBlocks)
+    trace_kernel(SceneView sc, FrameParams fp, RayQueue q, float4 *hits, WaveCounters *wc_closest, uint32_t slot_lo,
+                 uint32_t n_slots, ShadowQueue sq, float4 *accum, WaveCounters *wc_shadow, int min_active_closest,
+                 int min_active_shadow) {
+  __shared__ RayPool pools[kTraceBlock / 32];
+  RayPool *pool = &pools[threadIdx.x >> 5];
+  int lm[kLmSize];  // the lane's ray, best hit and traversal stack (see LaneTrav)
+  const bool closest_first = blockIdx.x & 1u;
+  for (int phase = 0; phase < 2; ++phase) {
+    if ((phase == 0) == closest_first) {
+      if (wc_closest) drain_closest<HAS_SHAPES, PRIMARY>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, min_active_closest, pool, lm);
+    } else {
+      if (wc_shadow) drain_shadow<HAS_SHAPES>(sc, sq, accum, wc_shadow, min_active_shadow, pool, lm);
+    }
   }
 }
 
@@ -717,15 +1039,15 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
 // Tail kernel.  Once a wave is small (a few thousand rays) every further wave costs the latency of its
 // SLOWEST ray plus two launches, and a foliage chain needs ~10 of them.  Here each lane follows its own
 // ray to the end instead — closest hit, shade, next bounce — so the tail costs the longest single
-// chain (max of sums) instead of the sum of per-wave maxima.  Shadow rays are queued and traced by one
-// launch afterwards; when a hit spawns both children the refraction ray is spilled to `qspill`
+// chain (max of sums) instead of the sum of per-wave maxima.  Shadow rays are appended to the queue (and
+// counter `wc_sh`) that already holds the last shade's untraced shadow rays; ONE launch traces them all afterwards; when a hit spawns both children the refraction ray is spilled to `qspill`
 // (processed by the next tail launch).
 // ---------------------------------------------------------------------------------------------
 template <bool HAS_SHAPES>
 __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : 4) tail_kernel(SceneView sc, FrameParams fp, RayQueue qin,
                                                                               WaveCounters *wc, RayQueue qspill,
                                                                               ShadowQueue sq, Counters *ctr,
-                                                                              float4 *accum) {
+                                                                              float4 *accum, WaveCounters *wc_sh) {
   const uint32_t lane = lane_id();
   const uint32_t count = wc[0].n_rays;
   const uint32_t S = (uint32_t)sc.shadow_samples;
@@ -748,7 +1070,7 @@ __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : 4) tail_kernel(S
           // lanes that reach this point together reserve their slots with ONE atomic (coalesced group)
           cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
           uint32_t sbase = 0;
-          if (g.thread_rank() == 0) sbase = atomicAdd(&wc[0].n_shadow, S * g.size());
+          if (g.thread_rank() == 0) sbase = atomicAdd(&wc_sh->n_shadow, S * g.size());
           sbase = g.shfl(sbase, 0) + S * g.thread_rank();
           emit_shadow_rays<HAS_SHAPES, true>(sc, fp, r, s, sq, sbase, ctr, accum);
         }
@@ -818,19 +1140,17 @@ __global__ void untile_kernel(const float *gathered, uint32_t n_ranks, uint32_t 
 // ---------------------------------------------------------------------------------------------
 void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue q, float4 *hits,
                   WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, ShadowQueue sq, float4 *accum,
-                  WaveCounters *wc_shadow, int grid, cudaStream_t st) {
+                  WaveCounters *wc_shadow, int min_active_closest, int min_active_shadow, int grid, cudaStream_t st) {
   if (!wc_closest && !wc_shadow) return;
+#define NRB_LAUNCH_TRACE(HS, PR)                                                                                       \
+  trace_kernel<HS, PR><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow, \
+                                                     min_active_closest, min_active_shadow)
   if (has_shapes) {
-    if (primary)
-      trace_kernel<true, true><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow);
-    else
-      trace_kernel<true, false><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow);
+    if (primary) NRB_LAUNCH_TRACE(true, true); else NRB_LAUNCH_TRACE(true, false);
   } else {
-    if (primary)
-      trace_kernel<false, true><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow);
-    else
-      trace_kernel<false, false><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow);
+    if (primary) NRB_LAUNCH_TRACE(false, true); else NRB_LAUNCH_TRACE(false, false);
   }
+#undef NRB_LAUNCH_TRACE
 }
 
 void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue qin,
@@ -851,11 +1171,12 @@ void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, b
 }
 
 void launch_tail(const SceneView &sc, bool has_shapes, const FrameParams &fp, RayQueue qin, WaveCounters *wc,
-                 RayQueue qspill, ShadowQueue sq, Counters *ctr, float4 *accum, int grid, cudaStream_t st) {
+                 RayQueue qspill, ShadowQueue sq, Counters *ctr, float4 *accum, WaveCounters *wc_sh, int grid,
+                 cudaStream_t st) {
   if (has_shapes)
-    tail_kernel<true><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum);
+    tail_kernel<true><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum, wc_sh);
   else
-    tail_kernel<false><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum);
+    tail_kernel<false><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum, wc_sh);
 }
 
 int shade_blocks_per_sm(bool has_shapes) {

@@ -11,6 +11,9 @@ constexpr int kTraceBlock = 128;
 #ifndef NRB_TRACE_MIN_BLOCKS
 #define NRB_TRACE_MIN_BLOCKS 9
 #endif
+#ifndef NRB_NODE_LOADS
+#define NRB_NODE_LOADS 1
+#endif
 constexpr int kFetchPackets = NRB_FETCH_PACKETS;  // 32-ray packets a warp takes per cursor atomic
 constexpr int kTraceMinBlocks = NRB_TRACE_MIN_BLOCKS;  // resident CTAs / SM the trace kernel is compiled for
 constexpr int kShadeBlock = 128;
@@ -18,12 +21,13 @@ constexpr int kShadeMinBlocks = 6;  // caps shade at 80 registers -> 768 residen
 
 void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue q, float4 *hits,
                   WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, ShadowQueue sq, float4 *accum,
-                  WaveCounters *wc_shadow, int grid, cudaStream_t st);
+                  WaveCounters *wc_shadow, int min_active_closest, int min_active_shadow, int grid, cudaStream_t st);
 void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue qin,
                   const float4 *hits, WaveCounters *wc, uint32_t slot_lo, uint32_t n_slots, uint32_t lo, uint32_t hi,
                   RayQueue qout, ShadowQueue sq, Counters *ctr, float4 *accum, int grid, cudaStream_t st);
 void launch_tail(const SceneView &sc, bool has_shapes, const FrameParams &fp, RayQueue qin, WaveCounters *wc,
-                 RayQueue qspill, ShadowQueue sq, Counters *ctr, float4 *accum, int grid, cudaStream_t st);
+                 RayQueue qspill, ShadowQueue sq, Counters *ctr, float4 *accum, WaveCounters *wc_sh, int grid,
+                 cudaStream_t st);
 int shade_blocks_per_sm(bool has_shapes);
 void launch_resolve(const float4 *accum, uint32_t n, uint32_t spp, float *out_rgb, cudaStream_t st);
 void launch_resolve_rgb8(const float4 *accum, uint32_t n, uint32_t spp, uint8_t *out, cudaStream_t st);

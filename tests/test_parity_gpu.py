@@ -252,9 +252,12 @@ def test_both_children_spill_and_area_light(gpu):
 
 
 @pytest.mark.parametrize("env", [dict(NRB_TAIL_RAYS=0), dict(NRB_TAIL_RAYS=1 << 30), dict(NRB_SHADOW_CAP=4096),
-                                 dict(NRB_BATCH_SLOTS=4096), dict(NRB_BATCH_SLOTS=4096, NRB_SHADOW_CAP=2048, NRB_TAIL_RAYS=64)])
+                                 dict(NRB_BATCH_SLOTS=4096), dict(NRB_BATCH_SLOTS=4096, NRB_SHADOW_CAP=2048, NRB_TAIL_RAYS=64),
+                                 dict(NRB_REFILL_PRIMARY=20, NRB_REFILL_RAYS=24, NRB_REFILL_SHADOW=24),
+                                 dict(NRB_REFILL_PRIMARY=31, NRB_REFILL_RAYS=31, NRB_REFILL_SHADOW=31, NRB_TAIL_RAYS=0)])
 def test_driver_paths_give_the_same_image(gpu, env):
-    """No tail / everything in the tail / chunked shadow queue / many batches: same frame as the default path."""
+    """No tail / everything in the tail / chunked shadow queue / many batches / dynamic fetch (warps refill their
+    idle lanes mid-packet): same frame as the default path."""
     nodes, lights = _glass_mirror_scene()
     base, st0, ref, ost = render_both(nodes, lights, eye=(0, 1.5, -5.5), w=96, h=80, spp=2, window=1.0, seed=8)
     with _Env(**env):
@@ -276,7 +279,8 @@ def test_mesh_scene_driver_paths(gpu):
         return out, st
 
     base, st0 = go()
-    for env in (dict(NRB_TAIL_RAYS=0), dict(NRB_TAIL_RAYS=1 << 30), dict(NRB_BATCH_SLOTS=8192), dict(NRB_SHADOW_CAP=1024)):
+    for env in (dict(NRB_TAIL_RAYS=0), dict(NRB_TAIL_RAYS=1 << 30), dict(NRB_BATCH_SLOTS=8192), dict(NRB_SHADOW_CAP=1024),
+                dict(NRB_REFILL_PRIMARY=16, NRB_REFILL_RAYS=20, NRB_REFILL_SHADOW=20)):
         with _Env(**env):
             img, st = go()
         np.testing.assert_allclose(img, base, rtol=0, atol=3e-5, err_msg=str(env))
