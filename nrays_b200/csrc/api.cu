@@ -656,6 +656,8 @@ int make_frame_params(const NrbCamera &cam, const NrbTileSet *tiles, FrameParams
   }
   double ws = std::max(std::fabs(A[3]), std::max(std::fabs(B[3]), std::fabs(Cc[3])));
   fp.wx = (float)(A[3] / ws), fp.wy = (float)(B[3] / ws), fp.w0 = (float)(Cc[3] / ws);
+  fp.div_spp = make_fastdiv(fp.spp), fp.div_tiles_x = make_fastdiv(fp.tiles_x), fp.div_width = make_fastdiv(fp.width);
+  fp.div_tile_stride = make_fastdiv(fp.tile_stride);
   fp.seed_lo = (uint32_t)cam.seed;
   fp.seed_hi = (uint32_t)(cam.seed >> 32);
   return NRB_OK;
@@ -1048,7 +1050,7 @@ int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOp
   S->build_info.gpu_build_ms = H.gpu_build_ms;
   S->build_info.builder = builder;
   S->grid_trace = S->sm_count * trace_blocks_per_sm(S->has_shapes);
-  S->grid_tail = S->sm_count * 4;
+  S->grid_tail = S->sm_count * (S->has_shapes ? 3 : kTailMinBlocks);
   S->grid_shade = S->sm_count * shade_blocks_per_sm(S->has_shapes);
   *out = S.release();
   return NRB_OK;

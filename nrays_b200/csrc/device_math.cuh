@@ -21,10 +21,18 @@ NRB_DI V3 cmul(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
 NRB_DI float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
 NRB_DI V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 NRB_DI V3 normalize(V3 a) {
-  float inv = 1.0f / sqrtf(dot(a, a));
+  float inv = 1.0f / sqrtf(dot(a, a));  // correctly rounded: ray directions decide silhouette / shadow-edge pixels
   return a * inv;
 }
+NRB_DI V3 normalize_fast(V3 a) { return a * rsqrtf(dot(a, a)); }  // MUFU.RSQ, <= 2 ulp: shading-only vectors
 NRB_DI float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+NRB_DI uint32_t fdiv(uint32_t n, const FastDiv &f) {  // n / f.d, exact (device_types.cuh)
+  if (f.d == 1u) return n;
+  unsigned long long lo = (unsigned long long)f.mul_lo * n;
+  unsigned long long hi = (unsigned long long)f.mul_hi * n + (lo >> 32);
+  return (uint32_t)(hi >> 32);
+}
 
 // ---- Philox4x32-10 (same function as the oracle; known-answer vectors in tests) -----------------
 NRB_DI void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
@@ -450,8 +458,8 @@ NRB_DI float4 tex_sample(const SceneView &sc, int tex, float cu, float cv) {
     ux = fminf(fmaxf(ux, 0.0f), 1.0f);
     uy = fminf(fmaxf(uy, 0.0f), 1.0f);
   } else {
-    ux = fmodf(ux, 1.0f);
-    uy = fmodf(uy, 1.0f);
+    ux = ux - truncf(ux);  // == fmodf(ux, 1.0f) bit for bit (the fraction of a float is exact), 2 instructions
+    uy = uy - truncf(uy);
     if (ux < 0.0f) ux = 1.0f + ux;
     if (uy < 0.0f) uy = 1.0f + uy;
   }

@@ -162,6 +162,24 @@ struct Counters {
   unsigned long long dbg_nodes, dbg_tris, dbg_rays;  // -DNRB_COUNT_VISITS builds only
 };
 
+// Exact division of a 32-bit number by a run-time constant: q = hi64(M * n), M = floor(2^64 / d) + 1
+// (Lemire et al.; exact for every 32-bit n and d >= 2).  Three instructions instead of a ~25-instruction
+// software division; the kernels divide by spp / tiles_x / width several times per ray.
+struct FastDiv {
+  uint32_t mul_lo, mul_hi;
+  uint32_t d;
+  uint32_t _pad;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  unsigned long long m = d >= 2 ? (~0ull / d) + 1ull : 0ull;  // floor((2^64 - 1) / d) + 1 == floor(2^64 / d) + 1 unless d | 2^64
+  if (d >= 2 && (d & (d - 1)) == 0) m = (1ull << 63) / (d >> 1);  // power of two: exactly 2^64 / d
+  f.mul_lo = (uint32_t)m, f.mul_hi = (uint32_t)(m >> 32);
+  f._pad = 0;
+  return f;
+}
+
 // Per-frame constants
 struct FrameParams {
   uint32_t width, height, spp, max_depth;
@@ -177,6 +195,7 @@ struct FrameParams {
   float dx[3], dy[3], d0[3];
   float wx, wy, w0;  // homogeneous w = wx * ndc.x + wy * ndc.y + w0; the direction flips when w < 0
   uint32_t seed_lo, seed_hi;
+  FastDiv div_spp, div_tiles_x, div_width, div_tile_stride;
 };
 
 }  // namespace nrb

@@ -33,9 +33,9 @@ NRB_DI uint32_t compact4(uint32_t v) {
 
 NRB_DI uint32_t accum_index(const FrameParams &fp, uint32_t ipt) {
   if (!fp.packed) return ipt;
-  uint32_t y = ipt / fp.width, x = ipt - y * fp.width;
+  uint32_t y = fdiv(ipt, fp.div_width), x = ipt - y * fp.width;
   uint32_t tile = (y / NRB_TILE) * fp.tiles_x + (x / NRB_TILE);
-  uint32_t lt = (tile - fp.tile_first) / fp.tile_stride;
+  uint32_t lt = fdiv(tile - fp.tile_first, fp.div_tile_stride);
   return lt * (NRB_TILE * NRB_TILE) + (y % NRB_TILE) * NRB_TILE + (x % NRB_TILE);
 }
 
@@ -52,11 +52,11 @@ NRB_DI void accum_add(float4 *accum, uint32_t idx, V3 c) {
 // tile, samples innermost, so a warp covers a compact pixel block.
 // ---------------------------------------------------------------------------------------------
 NRB_DI bool primary_ray(const FrameParams &fp, uint32_t slot, V3 &o, V3 &d, uint32_t &gid) {
-  uint32_t per_tile = NRB_TILE * NRB_TILE * fp.spp;
-  uint32_t lt = slot / per_tile, r = slot - lt * per_tile;
-  uint32_t p = r / fp.spp, s = r - p * fp.spp;
+  // slot = (local tile * 256 + pixel in tile) * spp + sample
+  uint32_t q = fdiv(slot, fp.div_spp), s = slot - q * fp.spp;
+  uint32_t lt = q / (NRB_TILE * NRB_TILE), p = q % (NRB_TILE * NRB_TILE);
   uint32_t tile = fp.tile_first + lt * fp.tile_stride;
-  uint32_t ty = tile / fp.tiles_x, tx = tile - ty * fp.tiles_x;
+  uint32_t ty = fdiv(tile, fp.div_tiles_x), tx = tile - ty * fp.tiles_x;
   uint32_t x = tx * NRB_TILE + compact4(p), y = ty * NRB_TILE + compact4(p >> 1);
   if (x >= fp.width || y >= fp.height) return false;
   uint32_t ipt = y * fp.width + x;
@@ -790,7 +790,7 @@ template <bool HAS_SHAPES>
 NRB_DI void shade_eval(const SceneView &sc, const FrameParams &fp, const RayState &r, float4 h, bool active,
                        float4 *accum, Shaded &out) {
   const uint32_t prim = __float_as_uint(h.y);
-  out.ipt = r.gid / fp.spp, out.smp = r.gid - out.ipt * fp.spp;
+  out.ipt = fdiv(r.gid, fp.div_spp), out.smp = r.gid - out.ipt * fp.spp;
   out.pix = active ? accum_index(fp, out.ipt) : 0u;
   const bool is_hit = active && prim != kMiss;
   if (active && !is_hit) {
@@ -864,9 +864,9 @@ NRB_DI void light_sample(const SceneView &sc, const FrameParams &fp, const RaySt
   float ndl = dot(ldir, s.n);
   float dcoeff = fmaxf(ndl, 0.0f);
   c = s.kd * dcoeff;
-  V3 rl = normalize(-ldir + s.n * (2.0f * ndl));
+  V3 rl = normalize_fast(-ldir + s.n * (2.0f * ndl));
   float scoeff = -dot(rl, r.d);
-  if (scoeff > 0.0f) c = c + s.ks * powf(scoeff, s.shininess);
+  if (scoeff > 0.0f) c = c + s.ks * __powf(scoeff, s.shininess);  // ex2(Ns * lg2(s)): rel. error ~2e-7 * Ns
   c = cmul(mk(L.color[0], L.color[1], L.color[2]), c) * (inv_ns * s.w_obj);
   so = s.pt + ldir * 0.001f;
 }
@@ -1044,7 +1044,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
 // (processed by the next tail launch).
 // ---------------------------------------------------------------------------------------------
 template <bool HAS_SHAPES>
-__global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : 4) tail_kernel(SceneView sc, FrameParams fp, RayQueue qin,
+__global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : kTailMinBlocks) tail_kernel(SceneView sc, FrameParams fp, RayQueue qin,
                                                                               WaveCounters *wc, RayQueue qspill,
                                                                               ShadowQueue sq, Counters *ctr,
                                                                               float4 *accum, WaveCounters *wc_sh) {

@@ -16,6 +16,10 @@ constexpr int kTraceBlock = 128;
 #endif
 constexpr int kFetchPackets = NRB_FETCH_PACKETS;  // 32-ray packets a warp takes per cursor atomic
 constexpr int kTraceMinBlocks = NRB_TRACE_MIN_BLOCKS;  // resident CTAs / SM the trace kernel is compiled for
+#ifndef NRB_TAIL_MIN_BLOCKS
+#define NRB_TAIL_MIN_BLOCKS 4
+#endif
+constexpr int kTailMinBlocks = NRB_TAIL_MIN_BLOCKS;  // resident CTAs / SM of the tail kernel (mesh-only scenes)
 constexpr int kShadeBlock = 128;
 constexpr int kShadeMinBlocks = 6;  // caps shade at 80 registers -> 768 resident threads / SM (8 spills too much)
 
