@@ -162,7 +162,7 @@ typedef struct NrbStats {
   uint64_t rays_primary;
   uint64_t rays_reflect;
   uint64_t rays_refract;
-  uint64_t rays_shadow;
+  uint64_t rays_shadow;     /* light samples of the reference semantics = shadow queries cast + rays_shadow_culled */
   uint64_t paths_truncated; /* children not spawned because of max_depth */
   uint32_t waves;           /* wavefront iterations */
   uint32_t kernel_launches; /* this library's kernels launched by the call */
@@ -175,7 +175,8 @@ typedef struct NrbStats {
   uint64_t scene_bytes;
   uint32_t launches_trace;  /* launches of the persistent trace kernel (ms_trace is their CUDA-event time) */
   uint32_t launches_shade;  /* launches of the shade kernel */
-  uint32_t _reserved[2];
+  uint64_t rays_shadow_culled; /* of rays_shadow: light samples whose contribution is exactly zero (weight 0, e.g. hits on
+                                * fully transparent texels) — the reference casts them, this library does not */
 } NrbStats;
 
 typedef struct NrbScene NrbScene; /* opaque handle == Arc<Scene> of the reference */

@@ -143,16 +143,23 @@ class NrbStats(C.Structure):
         ("scene_bytes", C.c_uint64),
         ("launches_trace", C.c_uint32),
         ("launches_shade", C.c_uint32),
-        ("_reserved", C.c_uint32 * 2),
+        ("rays_shadow_culled", C.c_uint64),
     ]
 
     @property
     def rays_total(self):
+        """BVH queries actually performed (the Mrays/s numerator)."""
+        return self.rays_primary + self.rays_reflect + self.rays_refract + self.rays_shadow - self.rays_shadow_culled
+
+    @property
+    def rays_reference(self):
+        """BVH queries of the reference semantics (it also casts the zero-weight light samples)."""
         return self.rays_primary + self.rays_reflect + self.rays_refract + self.rays_shadow
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("_")}
         d["rays_total"] = self.rays_total
+        d["rays_reference"] = self.rays_reference
         return d
 
 

@@ -960,6 +960,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
     stats->rays_reflect = S.h_counters->rays_reflect;
     stats->rays_refract = S.h_counters->rays_refract;
     stats->rays_shadow = S.h_counters->rays_shadow;
+    stats->rays_shadow_culled = S.h_counters->rays_shadow_culled;
     stats->paths_truncated = S.h_counters->paths_truncated;
     stats->waves = waves;
     stats->kernel_launches = launches;

@@ -156,6 +156,17 @@ NRB_DI void test_children(const NodeRec &n, const RayPre &p, float tbest, float 
   c1max = fminf(fminf(fmaf(n.n2.y, aidx, c1tx), fmaf(n.n2.z, aidy, c1ty)), fminf(fmaf(n.n2.w, aidz, c1tz), tbest));
 }
 
+// Slab test of one padded box [lo, hi] against the segment [0, tmax] with the ray's precomputed reciprocals — the
+// same arithmetic and padding as the node boxes (origin inside counts as a hit).
+NRB_DI bool box_hit(const RayPre &p, const float lo[3], const float hi[3], float tmax) {
+  float ax = fmaf(lo[0], p.idx, -p.oodx), bx = fmaf(hi[0], p.idx, -p.oodx);
+  float ay = fmaf(lo[1], p.idy, -p.oody), by = fmaf(hi[1], p.idy, -p.oody);
+  float az = fmaf(lo[2], p.idz, -p.oodz), bz = fmaf(hi[2], p.idz, -p.oodz);
+  float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+  float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+  return t1 >= t0;
+}
+
 // ANY = true: return at the first hit with toi <= tmax (shadow rays vs opaque geometry).
 // ANY = false: closest hit with toi < tmax (strict, best_first_search keeps the first of equals).
 template <bool HAS_SHAPES, bool ANY>
@@ -476,25 +487,11 @@ NRB_DI bool shadow_candidate(const SceneView &sc, int root, int node_id, V3 o, V
 template <bool HAS_SHAPES>
 NRB_DI bool shadow_candidates(const SceneView &sc, V3 o, V3 d, float tmax, V3 &filter) {
   bool occluded = false;
-  {
+  if (sc.n_candidates > 0) {
+    const RayPre pre = ray_pre(o, d);
     for (int c = 0; c < sc.n_candidates && !occluded; ++c) {
       const Candidate cd = sc.candidates[c];
-      // slab test against the candidate's box (bv cost), origin-inside counts as hit
-      float t0 = 0.0f, t1 = tmax;
-      bool miss = false;
-#pragma unroll
-      for (int ax = 0; ax < 3; ++ax) {
-        float oi = comp(o, ax), di = comp(d, ax);
-        if (di == 0.0f) {
-          if (oi < cd.lo[ax] || oi > cd.hi[ax]) miss = true;
-        } else {
-          float inv = 1.0f / di;
-          float ta = (cd.lo[ax] - oi) * inv, tb = (cd.hi[ax] - oi) * inv;
-          t0 = fmaxf(t0, fminf(ta, tb));
-          t1 = fminf(t1, fmaxf(ta, tb));
-        }
-      }
-      if (miss || t0 > t1) continue;
+      if (!box_hit(pre, cd.lo, cd.hi, tmax)) continue;  // bv cost of the candidate's box
       occluded = shadow_candidate<HAS_SHAPES>(sc, cd.root, cd.node, o, d, tmax, filter);
     }
   }
@@ -587,25 +584,9 @@ NRB_DI bool shadow_advance(const SceneView &sc, const ShadowQueue &sq, uint32_t 
   }
   if (cand + 1 < sc.n_candidates) {
     const float tmax = sq.a[idx].w;
-    const V3 o = lm_vec(lm, kLmO), d = lm_vec(lm, kLmD);
     for (++cand; cand < sc.n_candidates; ++cand) {
       const Candidate cd = sc.candidates[cand];
-      // slab test against the candidate's box (bv cost), origin-inside counts as hit
-      float t0 = 0.0f, t1 = tmax;
-      bool miss = false;
-#pragma unroll
-      for (int ax = 0; ax < 3; ++ax) {
-        float oi = comp(o, ax), di = comp(d, ax);
-        if (di == 0.0f) {
-          if (oi < cd.lo[ax] || oi > cd.hi[ax]) miss = true;
-        } else {
-          float inv = 1.0f / di;
-          float ta = (cd.lo[ax] - oi) * inv, tb = (cd.hi[ax] - oi) * inv;
-          t0 = fmaxf(t0, fminf(ta, tb));
-          t1 = fminf(t1, fmaxf(ta, tb));
-        }
-      }
-      if (miss || t0 > t1) continue;
+      if (!box_hit(s.pre, cd.lo, cd.hi, tmax)) continue;  // bv cost of the candidate's box
       trav_start(s, lm, cd.root, nextafterf(tmax, 3.402823466e+38f));  // closest hit with toi <= tmax
       return true;
     }
@@ -781,7 +762,7 @@ struct Shaded {
   float alpha, a1;  // alpha = obj.w * node.alpha; a' = alpha == 1 ? 1 : alpha
   float refl_mix, refl_att, refr_coeff;
   uint32_t pix, ipt, smp;
-  bool emit_sh, want_refl, want_refr, trunc_refl, trunc_refr;
+  bool emit_sh, cull_sh, want_refl, want_refr, trunc_refl, trunc_refr;
 };
 
 // Material evaluation + the combine weights of Scene::trace (src/scene.rs:171-190).  Adds the
@@ -836,7 +817,11 @@ NRB_DI void shade_eval(const SceneView &sc, const FrameParams &fp, const RayStat
   out.w_obj = r.weight * out.a1 * (1.0f - ni.refl_mix);
   out.refl_mix = ni.refl_mix, out.refl_att = ni.refl_att, out.refr_coeff = ni.refr_coeff;
   if (is_hit) accum_add(accum, out.pix, obj_rgb * out.w_obj);
-  out.emit_sh = is_hit && phong && sc.shadow_samples > 0;
+  // PhongMaterial::compute queries every light sample; a sample whose weight w * a' * (1 - mix) is exactly zero (a hit
+  // on a fully transparent texel, a perfect mirror) adds exactly nothing, so its shadow query is not cast (counted apart)
+  const bool lit = is_hit && phong && sc.shadow_samples > 0;
+  out.emit_sh = lit && out.w_obj != 0.0f;
+  out.cull_sh = lit && !out.emit_sh;
   // reflection (Scene::trace_reflection, src/scene.rs:196-218)
   bool want_refl = is_hit && ni.refl_mix != 0.0f && r.energy > 0.1f;
   out.trunc_refl = want_refl && (r.depth + 1u >= fp.max_depth);
@@ -939,13 +924,15 @@ struct ShadeShared {
   uint32_t base[2];  // their first slots in the global queues
 };
 
-NRB_DI void flush_stats(Counters *ctr, uint32_t c_shadow, uint32_t c_refl, uint32_t c_refr, uint32_t c_trunc) {
+NRB_DI void flush_stats(Counters *ctr, uint32_t c_shadow, uint32_t c_refl, uint32_t c_refr, uint32_t c_trunc, uint32_t c_culled) {
   c_shadow = __reduce_add_sync(0xFFFFFFFFu, c_shadow);
+  c_culled = __reduce_add_sync(0xFFFFFFFFu, c_culled);
   c_refl = __reduce_add_sync(0xFFFFFFFFu, c_refl);
   c_refr = __reduce_add_sync(0xFFFFFFFFu, c_refr);
   c_trunc = __reduce_add_sync(0xFFFFFFFFu, c_trunc);
   if (lane_id() == 0) {
     if (c_shadow) atomicAdd(&ctr->rays_shadow, (unsigned long long)c_shadow);
+    if (c_culled) atomicAdd(&ctr->rays_shadow_culled, (unsigned long long)c_culled);
     if (c_refl) atomicAdd(&ctr->rays_reflect, (unsigned long long)c_refl);
     if (c_refr) atomicAdd(&ctr->rays_refract, (unsigned long long)c_refr);
     if (c_trunc) atomicAdd(&ctr->paths_truncated, (unsigned long long)c_trunc);
@@ -969,7 +956,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
   const uint32_t lane = lane_id();
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t S = (uint32_t)sc.shadow_samples;
-  uint32_t c_shadow = 0, c_refl = 0, c_refr = 0, c_trunc = 0;
+  uint32_t c_shadow = 0, c_refl = 0, c_refr = 0, c_trunc = 0, c_culled = 0;
 
   for (uint32_t bb = lo + blockIdx.x * blockDim.x; bb < end; bb += stride) {  // block-uniform trip count
     const uint32_t i = bb + threadIdx.x;
@@ -991,7 +978,8 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
     c_trunc += (s.trunc_refl ? 1u : 0u) + (s.trunc_refr ? 1u : 0u);
     c_refl += s.want_refl ? 1u : 0u;
     c_refr += s.want_refr ? 1u : 0u;
-    c_shadow += s.emit_sh ? S : 0u;
+    c_shadow += (s.emit_sh || s.cull_sh) ? S : 0u;
+    c_culled += s.cull_sh ? S : 0u;
 
     // ---- reserve queue slots: warp ballots -> shared-memory totals -> one global atomic per block ----
     const uint32_t m_sh = __ballot_sync(0xFFFFFFFFu, s.emit_sh);
@@ -1032,7 +1020,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
         ctr->overflow = 1u;
     }
   }
-  flush_stats(ctr, c_shadow, c_refl, c_refr, c_trunc);
+  flush_stats(ctr, c_shadow, c_refl, c_refr, c_trunc, c_culled);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1051,7 +1039,7 @@ __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : kTailMinBlocks) 
   const uint32_t lane = lane_id();
   const uint32_t count = wc[0].n_rays;
   const uint32_t S = (uint32_t)sc.shadow_samples;
-  uint32_t c_shadow = 0, c_refl = 0, c_refr = 0, c_trunc = 0;
+  uint32_t c_shadow = 0, c_refl = 0, c_refr = 0, c_trunc = 0, c_culled = 0;
   while (true) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(&wc[0].fetch_closest, 32u);
@@ -1065,6 +1053,7 @@ __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : kTailMinBlocks) 
         Shaded s;
         shade_eval<HAS_SHAPES>(sc, fp, r, h, true, accum, s);
         c_trunc += (s.trunc_refl ? 1u : 0u) + (s.trunc_refr ? 1u : 0u);
+        if (s.cull_sh) c_shadow += S, c_culled += S;
         if (s.emit_sh) {
           c_shadow += S;
           // lanes that reach this point together reserve their slots with ONE atomic (coalesced group)
@@ -1094,7 +1083,7 @@ __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : kTailMinBlocks) 
       }
     }
   }
-  flush_stats(ctr, c_shadow, c_refl, c_refr, c_trunc);
+  flush_stats(ctr, c_shadow, c_refl, c_refr, c_trunc, c_culled);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -21,7 +21,10 @@ constexpr int kTraceMinBlocks = NRB_TRACE_MIN_BLOCKS;  // resident CTAs / SM the
 #endif
 constexpr int kTailMinBlocks = NRB_TAIL_MIN_BLOCKS;  // resident CTAs / SM of the tail kernel (mesh-only scenes)
 constexpr int kShadeBlock = 128;
-constexpr int kShadeMinBlocks = 6;  // caps shade at 80 registers -> 768 resident threads / SM (8 spills too much)
+#ifndef NRB_SHADE_MIN_BLOCKS
+#define NRB_SHADE_MIN_BLOCKS 6
+#endif
+constexpr int kShadeMinBlocks = NRB_SHADE_MIN_BLOCKS;  // 6: shade capped at 80 registers -> 768 resident threads / SM
 
 void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue q, float4 *hits,
                   WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, ShadowQueue sq, float4 *accum,

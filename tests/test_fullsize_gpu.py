@@ -95,7 +95,7 @@ def test_c1_reference_config_against_oracle(gpu):
         ref, ost = O.OracleScene(scene.flat, 64).render(cam)
         m = image_metrics(img, ref)
         assert m["frac_over"] <= 1e-3, m
-        assert abs(int(st.rays_total) - int(ost.rays_total)) <= 1e-3 * ost.rays_total
+        assert abs(int(st.rays_reference) - int(ost.rays_reference)) <= 1e-3 * ost.rays_reference
         scene.close()
 
 

@@ -88,7 +88,10 @@ def test_alpha_mapped_mesh_and_per_node_shadow_semantics(gpu):
              node(TriMesh(P + np.float32([0, 1.2, 0]), F, UV), phong(ka=(0.5, 0.2, 0.2)), alpha=0.4)]
     img, st, ref, ost = render_both(nodes, [Light((0.5, 6, -0.5), 0.0, 1, (1, 1, 1))], eye=(0.0, 3.0, -6.0), w=160, h=120)
     assert_parity(img, ref, max_frac=2e-3, what="alpha map")
-    assert_counts_close(st, ost)
+    assert_counts_close(st, ost)   # rays_shadow counts the reference's light samples, cast or not
+    # hits on fully transparent texels carry weight 0: their light samples add exactly nothing and are not cast
+    assert 0 < st.rays_shadow_culled < st.rays_shadow and ost.rays_shadow_culled == 0
+    assert st.rays_total == st.rays_reference - st.rays_shadow_culled
 
 
 def test_solid_flag_and_camera_inside_objects(gpu):
