@@ -735,6 +735,8 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   // still traversing (0 = only when all 32 are done).  Measured (profiles/README.md): on the coherent headline
   // config every non-zero setting loses 8-25 % (the refill rounds cost more than the idle lanes), on the incoherent
   // hairball 20 lanes for shadow rays gains ~7 %; the default keeps whole packets.
+  // opaque any-hit phase of shadow rays walked from the light end (rays of one point light leave together)
+  const int reverse_shadow = (int)env_size("NRB_REVERSE_SHADOW", 1);
   const int refill_primary = (int)env_size("NRB_REFILL_PRIMARY", 0);
   const int refill_rays = (int)env_size("NRB_REFILL_RAYS", 0);
   const int refill_shadow = (int)env_size("NRB_REFILL_SHADOW", 0);
@@ -773,7 +775,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
       cudaEvent_t e0 = get_event(S, ev_used), e1 = get_event(S, ev_used);
       CU(cudaEventRecord(e0, st));
       launch_trace(S.view, S.has_shapes, fp, primary, q, S.d_hits.as<float4>(), wcc, slot_lo, n_slots, sq, accum, wcs,
-                   primary ? refill_primary : refill_rays, refill_shadow, S.grid_trace, st);
+                   primary ? refill_primary : refill_rays, refill_shadow, reverse_shadow, S.grid_trace, st);
       CU(cudaEventRecord(e1, st));
       trace_spans.emplace_back(e0, e1);
       ++launches;

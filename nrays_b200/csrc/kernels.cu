@@ -558,10 +558,21 @@ NRB_DI void shadow_ray(const SceneView &sc, const ShadowQueue &q, uint32_t i, fl
 // traversal was started, false if the ray is finished (occluded, or accumulated into its pixel).
 template <bool HAS_SHAPES>
 NRB_DI bool shadow_advance(const SceneView &sc, const ShadowQueue &sq, uint32_t idx, LaneTrav &s, int *lm, int &cand,
-                           bool first, float4 *accum) {
+                           bool first, bool reverse, float4 *accum) {
   // The transparent filter is folded into the entry's contribution in place (the entry belongs to this lane),
   // so the state carried across trav_run calls is just (idx, cand).
-  const uint32_t prim = (uint32_t)lm[kLmPrim];
+  // reverse: the opaque any-hit phase walks the segment from its LIGHT end.  Occlusion of a segment does not
+  // depend on the direction it is walked in, but rays that leave one point light together visit the same nodes
+  // in the same order, like primary rays, instead of starting at scattered surface points.  The candidate
+  // phases need the hit closest to the surface and always use the forward ray.
+  const uint32_t prim = first ? kMiss : (uint32_t)lm[kLmPrim];
+  if (first || (cand < 0 && prim == kMiss && reverse && sc.n_candidates > 0)) {
+    const float4 a = sq.a[idx], b = sq.b[idx];
+    V3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
+    if (first && reverse && sc.root_opaque != kEmpty) o = o + d * a.w, d = -d;
+    lm_set_ray(lm, o, d);
+    s.pre = ray_pre(o, d);
+  }
   if (first) {
     cand = -1;
     if (sc.root_opaque != kEmpty) {
@@ -619,7 +630,7 @@ NRB_DI bool shadow_planes(const SceneView &sc, const ShadowQueue &sq, uint32_t i
 
 template <bool HAS_SHAPES>
 NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *accum, WaveCounters *wc_shadow, int min_active,
-                         RayPool *pool, int *lm) {
+                         bool reverse, RayPool *pool, int *lm) {
   const uint32_t count = min(wc_shadow->n_shadow, sq.capacity);
   LaneTrav s;
   s.node = kEmpty;
@@ -631,13 +642,12 @@ NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *acc
     const uint32_t mine = pool_assign(pool, !active, &wc_shadow->fetch_shadow, count);
     if (mine != kNoRay) {
       idx = mine;
-      const float4 a = sq.a[idx], b = sq.b[idx];
-      const V3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
-      lm_set_ray(lm, o, d);
-      s.pre = ray_pre(o, d);
       bool occluded = false;
-      if (HAS_SHAPES) occluded = shadow_planes(sc, sq, idx, o, d, a.w);
-      active = !occluded && shadow_advance<HAS_SHAPES>(sc, sq, idx, s, lm, cand, true, accum);
+      if (HAS_SHAPES) {
+        const float4 a = sq.a[idx], b = sq.b[idx];
+        occluded = shadow_planes(sc, sq, idx, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), a.w);
+      }
+      active = !occluded && shadow_advance<HAS_SHAPES>(sc, sq, idx, s, lm, cand, true, reverse, accum);
     }
     if (__ballot_sync(0xFFFFFFFFu, active) == 0u) {
       if (pool_empty(pool)) break;
@@ -645,7 +655,7 @@ NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *acc
     }
     if (active) {
       trav_run<HAS_SHAPES>(sc, s, lm, cand < 0, min_active);
-      if (s.node == kEmpty) active = shadow_advance<HAS_SHAPES>(sc, sq, idx, s, lm, cand, false, accum);
+      if (s.node == kEmpty) active = shadow_advance<HAS_SHAPES>(sc, sq, idx, s, lm, cand, false, reverse, accum);
     }
   }
 }
@@ -715,7 +725,7 @@ template <bool HAS_SHAPES, bool PRIMARY>
 __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 6 : kTraceMinBlocks)
     trace_kernel(SceneView sc, FrameParams fp, RayQueue q, float4 *hits, WaveCounters *wc_closest, uint32_t slot_lo,
                  uint32_t n_slots, ShadowQueue sq, float4 *accum, WaveCounters *wc_shadow, int min_active_closest,
-                 int min_active_shadow) {
+                 int min_active_shadow, int reverse_shadow) {
   __shared__ RayPool pools[kTraceBlock / 32];
   RayPool *pool = &pools[threadIdx.x >> 5];
   int lm[kLmSize];  // the lane's ray, best hit and traversal stack (see LaneTrav)
@@ -724,7 +734,7 @@ __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 6 : kTraceMinBlocks)
     if ((phase == 0) == closest_first) {
       if (wc_closest) drain_closest<HAS_SHAPES, PRIMARY>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, min_active_closest, pool, lm);
     } else {
-      if (wc_shadow) drain_shadow<HAS_SHAPES>(sc, sq, accum, wc_shadow, min_active_shadow, pool, lm);
+      if (wc_shadow) drain_shadow<HAS_SHAPES>(sc, sq, accum, wc_shadow, min_active_shadow, reverse_shadow != 0, pool, lm);
     }
   }
 }
@@ -1129,11 +1139,12 @@ __global__ void untile_kernel(const float *gathered, uint32_t n_ranks, uint32_t 
 // ---------------------------------------------------------------------------------------------
 void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue q, float4 *hits,
                   WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, ShadowQueue sq, float4 *accum,
-                  WaveCounters *wc_shadow, int min_active_closest, int min_active_shadow, int grid, cudaStream_t st) {
+                  WaveCounters *wc_shadow, int min_active_closest, int min_active_shadow, int reverse_shadow, int grid,
+                  cudaStream_t st) {
   if (!wc_closest && !wc_shadow) return;
 #define NRB_LAUNCH_TRACE(HS, PR)                                                                                       \
   trace_kernel<HS, PR><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow, \
-                                                     min_active_closest, min_active_shadow)
+                                                     min_active_closest, min_active_shadow, reverse_shadow)
   if (has_shapes) {
     if (primary) NRB_LAUNCH_TRACE(true, true); else NRB_LAUNCH_TRACE(true, false);
   } else {

@@ -28,7 +28,8 @@ constexpr int kShadeMinBlocks = NRB_SHADE_MIN_BLOCKS;  // 6: shade capped at 80 
 
 void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue q, float4 *hits,
                   WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, ShadowQueue sq, float4 *accum,
-                  WaveCounters *wc_shadow, int min_active_closest, int min_active_shadow, int grid, cudaStream_t st);
+                  WaveCounters *wc_shadow, int min_active_closest, int min_active_shadow, int reverse_shadow, int grid,
+                  cudaStream_t st);
 void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue qin,
                   const float4 *hits, WaveCounters *wc, uint32_t slot_lo, uint32_t n_slots, uint32_t lo, uint32_t hi,
                   RayQueue qout, ShadowQueue sq, Counters *ctr, float4 *accum, int grid, cudaStream_t st);

@@ -256,6 +256,7 @@ def test_both_children_spill_and_area_light(gpu):
 
 @pytest.mark.parametrize("env", [dict(NRB_TAIL_RAYS=0), dict(NRB_TAIL_RAYS=1 << 30), dict(NRB_SHADOW_CAP=4096),
                                  dict(NRB_BATCH_SLOTS=4096), dict(NRB_BATCH_SLOTS=4096, NRB_SHADOW_CAP=2048, NRB_TAIL_RAYS=64),
+                                 dict(NRB_REVERSE_SHADOW=0),
                                  dict(NRB_REFILL_PRIMARY=20, NRB_REFILL_RAYS=24, NRB_REFILL_SHADOW=24),
                                  dict(NRB_REFILL_PRIMARY=31, NRB_REFILL_RAYS=31, NRB_REFILL_SHADOW=31, NRB_TAIL_RAYS=0)])
 def test_driver_paths_give_the_same_image(gpu, env):
@@ -283,7 +284,7 @@ def test_mesh_scene_driver_paths(gpu):
 
     base, st0 = go()
     for env in (dict(NRB_TAIL_RAYS=0), dict(NRB_TAIL_RAYS=1 << 30), dict(NRB_BATCH_SLOTS=8192), dict(NRB_SHADOW_CAP=1024),
-                dict(NRB_REFILL_PRIMARY=16, NRB_REFILL_RAYS=20, NRB_REFILL_SHADOW=20)):
+                dict(NRB_REFILL_PRIMARY=16, NRB_REFILL_RAYS=20, NRB_REFILL_SHADOW=20), dict(NRB_REVERSE_SHADOW=0)):
         with _Env(**env):
             img, st = go()
         np.testing.assert_allclose(img, base, rtol=0, atol=3e-5, err_msg=str(env))
