@@ -269,7 +269,7 @@ def run_ours(args, rank, local_rank, world):
         return float(t.item()), float(r.item())
 
     def reduce_counts(stats):
-        keys = ("rays_primary", "rays_reflect", "rays_refract", "rays_shadow")
+        keys = ("rays_primary", "rays_reflect", "rays_refract", "rays_shadow", "rays_shadow_culled")
         t = torch.tensor([float(sum(s[k] for s, _ in stats)) for k in keys], dtype=torch.float64, device=dev)
         if world > 1:
             td.all_reduce(t, op=td.ReduceOp.SUM)
@@ -288,7 +288,7 @@ def run_ours(args, rank, local_rank, world):
         s0 = stats_dev[0][0]
         geom_bytes = s0["bvh_nodes"] * 64 + s0["triangles"] * 48
         n_closest = sum(s["rays_primary"] + s["rays_reflect"] + s["rays_refract"] for s, _ in stats_dev)
-        n_shadow = sum(s["rays_shadow"] for s, _ in stats_dev)
+        n_shadow = sum(s["rays_shadow"] - s["rays_shadow_culled"] for s, _ in stats_dev)  # shadow queries actually cast
         # dominant kernel: the persistent trace kernel (closest hits read 32 B of ray + write a 16 B hit
         # record; wave 0 generates its rays on chip: 16 B; shadow rays read 48 B + one 16 B RED)
         ms_k = sum(s["ms_trace"] for s, _ in stats_dev)
@@ -300,13 +300,14 @@ def run_ours(args, rank, local_rank, world):
         bytes_k = 16 * n_primary_k + 48 * (n_closest - n_primary_k) + 64 * n_shadow + l_k * geom_bytes
         achieved = bytes_k / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
         # frame-level figure of SURVEY 8d over the WHOLE job: 160 B per ray + 16 B per primary + the scene once per rank and frame
-        n_all = sum(counts_all.values())
+        n_all = sum(counts_all.values()) - 2 * counts_all["rays_shadow_culled"]   # rays traced (culled light samples are in rays_shadow)
         frame_bytes = 160 * n_all + 16 * counts_all["rays_primary"] + world * len(stats_dev) * s0["scene_bytes"]
-        traffic = None
+        traffic, ncu_note = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(kname)
+                tj = json.load(open(tp))
+                traffic, ncu_note = tj.get(kname), tj.get("limiter")
             except Exception:
                 traffic = None
         roofline = {
@@ -314,6 +315,7 @@ def run_ours(args, rank, local_rank, world):
             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
             "bytes_per_launch": bytes_k / max(1, l_k), "ms_per_launch": ms_k / max(1, l_k),
             "kernel_share_of_step": ms_k / ms_dev if ms_dev > 0 else None,
+            "limiter_ncu": ncu_note,   # what actually bounds the kernel (ncu, profiles/): not HBM
             "frame": {"algorithmic_bytes_per_step": frame_bytes / len(stats_dev),
                       "achieved": frame_bytes / (ms_dev_max * 1e-3) / 1e9, "peak": peak * world,
                       "frac": frame_bytes / (ms_dev_max * 1e-3) / 1e9 / (peak * world)},
@@ -330,7 +332,11 @@ def run_ours(args, rank, local_rank, world):
             "config": {"workload": cfg["name"], "resolution": [w, h], "spp": spp, "window": window,
                        "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
                        "sharding": "none" if world == 1 else "16x16 tiles round-robin over %d ranks + one NCCL all-gather" % world,
-                       "rays_per_step": rays_dev / args.steps},
+                       "rays_per_step": rays_dev / args.steps,
+                       "rays_reference_per_step": (counts_all["rays_primary"] + counts_all["rays_reflect"] + counts_all["rays_refract"] +
+                                                   counts_all["rays_shadow"]) / args.steps,
+                       "note": "value counts BVH queries actually performed; the reference also casts the light samples of "
+                               "zero weight (rays_reference_per_step), which this library skips"},
             "e2e": {"value": rays_e2e / (ms_e2e_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(A.NrbCamera),
                     "d2h_bytes_per_step": w * h * 3 * 4, "ms_per_step": ms_e2e_max / args.steps},
             "gpu_launches": int(lt.item()),
