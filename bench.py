@@ -195,6 +195,18 @@ def run_ours(args, rank, local_rank, world):
     out = torch.empty(h * w * 3, dtype=torch.float32, device=dev)
     tpr = dist.tiles_per_rank(w, h, world)
     packed = torch.zeros((tpr, 16, 16, 3), dtype=torch.float32, device=dev) if world > 1 else None
+    # N > 1: every rank's resolve kernel stores its finished tiles straight into rank 0's image over NVLink (CUDA IPC
+    # mapping); if the mapping cannot be made the ranks fall back to ONE NCCL all-gather of packed tiles + un-tile.
+    peer = None
+    if world > 1 and os.environ.get("NRB_BENCH_EXCHANGE", "peer") == "peer":
+        try:
+            peer = dist.PeerImage(w, h, rank, world, local_rank)
+            if rank == 0:
+                out = peer.tensor()
+        except RuntimeError as e:
+            if rank == 0:
+                print("bench: peer image unavailable (%s), using the all-gather exchange" % e, file=sys.stderr)
+            peer = None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     host_ptr = lib.nrb_host_alloc(h * w * 3 * 4)  # pinned destination of the e2e image
     host_img = np.ctypeslib.as_array(C.cast(host_ptr, C.POINTER(C.c_float)), shape=(h * w * 3,))
@@ -207,6 +219,10 @@ def run_ours(args, rank, local_rank, world):
         cam = cam_for(step)
         if world == 1:
             return dist.render_device(scene, cam, out), 0
+        if peer is not None:
+            st = dist.render_tiles_to_image(scene, cam, rank, world, peer.ptr)
+            peer.sync()   # one 4-byte all-reduce: rank 0's next work sees every rank's pixels
+            return st, 0
         st, _n = dist.render_tiles_device(scene, cam, rank, world, packed)
         g = dist.all_gather_tiles(packed, world)
         if rank == 0:
@@ -248,6 +264,16 @@ def run_ours(args, rank, local_rank, world):
 
     for i in range(args.warmup):
         step_device(1000 + i)
+    verified = None
+    if world > 1:
+        # untimed check of the sharded frame against this GPU's own full-frame render of the same camera
+        step_device(999)
+        barrier()
+        if rank == 0:
+            ref_img = torch.empty(h * w * 3, dtype=torch.float32, device=dev)
+            dist.render_device(scene, cam_for(999), ref_img)
+            verified = bool((out - ref_img).abs().max().item() < 1e-4)
+        barrier()
     for i in range(max(1, min(args.warmup, 2))):
         step_e2e(2000 + i)
 
@@ -331,7 +357,11 @@ def run_ours(args, rank, local_rank, world):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["name"], "resolution": [w, h], "spp": spp, "window": window,
                        "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
-                       "sharding": "none" if world == 1 else "16x16 tiles round-robin over %d ranks + one NCCL all-gather" % world,
+                       "sharding": "none" if world == 1 else (
+                           "16x16 tiles round-robin over %d ranks; " % world +
+                           ("each rank's resolve kernel stores its tiles into rank 0's image over NVLink (CUDA IPC) + one 4-byte all-reduce"
+                            if peer is not None else "one NCCL all-gather of packed tiles + un-tile")),
+                       "sharded_frame_equals_single_gpu_frame": verified,
                        "rays_per_step": rays_dev / args.steps,
                        "rays_reference_per_step": (counts_all["rays_primary"] + counts_all["rays_reflect"] + counts_all["rays_refract"] +
                                                    counts_all["rays_shadow"]) / args.steps,
@@ -346,6 +376,10 @@ def run_ours(args, rank, local_rank, world):
         }
         print(json.dumps(line), flush=True)
     lib.nrb_host_free(host_ptr)
+    if peer is not None:
+        out = None
+        barrier()
+        peer.close()
     scene.close()
     if world > 1:
         td.destroy_process_group()

@@ -246,6 +246,24 @@ int nrb_render_device(NrbScene *scene, const NrbCamera *camera, float *d_out_rgb
 int nrb_render_tiles_device(NrbScene *scene, const NrbCamera *camera, const NrbTileSet *tiles,
                             float *d_out_tiles, uint32_t *n_local_tiles, NrbStats *stats);
 
+/* Tile-sharded render that resolves this rank's tiles straight into the ROW-MAJOR image `d_image_rgb`
+ * (width*height*3 floats, layout of nrb_render_device) and writes only the pixels it owns.  The image may live on
+ * ANOTHER GPU (memory opened with nrb_ipc_open): the finished pixels then cross NVLink once, in the resolve
+ * kernel itself, and no gather / un-tile pass follows (the one exchange of SURVEY 8e, fused into K5).  The
+ * caller orders the ranks (e.g. one tiny all-reduce) before the owner reads the image. */
+int nrb_render_tiles_to_image(NrbScene *scene, const NrbCamera *camera, const NrbTileSet *tiles, float *d_image_rgb,
+                              NrbStats *stats);
+
+/* Device memory that other processes on the node can map (one process per GPU): the owner allocates and
+ * passes the 64-byte handle around (any transport), peers open it and get a pointer valid in their kernels. */
+typedef struct NrbIpcHandle {
+  unsigned char bytes[64];
+} NrbIpcHandle;
+int nrb_ipc_alloc(int device, uint64_t bytes, void **d_ptr, NrbIpcHandle *handle); /* zero-filled */
+int nrb_ipc_open(int device, const NrbIpcHandle *handle, void **d_ptr);            /* in ANOTHER process than the owner */
+int nrb_ipc_close(int device, void *d_ptr);
+int nrb_ipc_free(int device, void *d_ptr);
+
 /* Number of 16x16 tiles covering width x height, and how many of them a tile set owns. */
 uint32_t nrb_tile_count(uint32_t width, uint32_t height);
 uint32_t nrb_tile_count_local(uint32_t width, uint32_t height, const NrbTileSet *tiles);

@@ -177,6 +177,10 @@ class NrbBuildInfo(C.Structure):
     ]
 
 
+class NrbIpcHandle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 64)]
+
+
 class NrbBuildOptions(C.Structure):
     _fields_ = [("builder", C.c_uint32), ("_reserved", C.c_uint32 * 3)]
 
@@ -198,6 +202,11 @@ EXPORTS = [
     "nrb_render",
     "nrb_render_device",
     "nrb_render_tiles_device",
+    "nrb_render_tiles_to_image",
+    "nrb_ipc_alloc",
+    "nrb_ipc_open",
+    "nrb_ipc_close",
+    "nrb_ipc_free",
     "nrb_tile_count",
     "nrb_tile_count_local",
     "nrb_untile_device",

@@ -50,6 +50,16 @@ def load():
     lib.nrb_render_tiles_device.argtypes = [vp, C.POINTER(A.NrbCamera), C.POINTER(A.NrbTileSet), vp,
                                             C.POINTER(u32), C.POINTER(A.NrbStats)]
     lib.nrb_render_tiles_device.restype = C.c_int
+    lib.nrb_render_tiles_to_image.argtypes = [vp, C.POINTER(A.NrbCamera), C.POINTER(A.NrbTileSet), vp, C.POINTER(A.NrbStats)]
+    lib.nrb_render_tiles_to_image.restype = C.c_int
+    lib.nrb_ipc_alloc.argtypes = [C.c_int, C.c_uint64, C.POINTER(vp), C.POINTER(A.NrbIpcHandle)]
+    lib.nrb_ipc_alloc.restype = C.c_int
+    lib.nrb_ipc_open.argtypes = [C.c_int, C.POINTER(A.NrbIpcHandle), C.POINTER(vp)]
+    lib.nrb_ipc_open.restype = C.c_int
+    lib.nrb_ipc_close.argtypes = [C.c_int, vp]
+    lib.nrb_ipc_close.restype = C.c_int
+    lib.nrb_ipc_free.argtypes = [C.c_int, vp]
+    lib.nrb_ipc_free.restype = C.c_int
     lib.nrb_tile_count.argtypes = [u32, u32]
     lib.nrb_tile_count.restype = u32
     lib.nrb_tile_count_local.argtypes = [u32, u32, C.POINTER(A.NrbTileSet)]

@@ -688,8 +688,10 @@ cudaEvent_t get_event(NrbScene &S, size_t &used) {
 }
 
 // Renders into S.d_accum and resolves to `d_out` (device; float rgb or u8 rgb).
+// `to_image`: with a tile set, resolve this rank's tiles into the row-major image `d_out` (possibly peer memory)
+// instead of the packed tile buffer.
 int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, float *d_out, uint8_t *d_out8,
-                  uint32_t *n_local_tiles, NrbStats *stats) {
+                  uint32_t *n_local_tiles, NrbStats *stats, bool to_image = false) {
   CU(cudaSetDevice(S.device));
   FrameParams fp;
   int rc = make_frame_params(cam, tiles, fp);
@@ -929,6 +931,8 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   }
   if (d_out8)
     launch_resolve_rgb8(accum, n_acc, fp.spp, d_out8, st);
+  else if (to_image && fp.packed)
+    launch_resolve_tiles_to_image(accum, fp, d_out, st);
   else
     launch_resolve(accum, n_acc, fp.spp, d_out, st);
   ++launches;
@@ -1147,6 +1151,59 @@ int nrb_render_tiles_device(NrbScene *scene, const NrbCamera *camera, const NrbT
                             uint32_t *n_local_tiles, NrbStats *stats) {
   if (!scene || !camera || !tiles || !d_out_tiles) return fail(NRB_ERR_INVALID_ARG, "scene/camera/tiles/out is NULL");
   return render_device(*scene, *camera, tiles, d_out_tiles, nullptr, n_local_tiles, stats);
+}
+
+int nrb_render_tiles_to_image(NrbScene *scene, const NrbCamera *camera, const NrbTileSet *tiles, float *d_image_rgb,
+                              NrbStats *stats) {
+  if (!scene || !camera || !tiles || !d_image_rgb) return fail(NRB_ERR_INVALID_ARG, "scene/camera/tiles/image is NULL");
+  return render_device(*scene, *camera, tiles, d_image_rgb, nullptr, nullptr, stats, true);
+}
+
+int nrb_ipc_alloc(int device, uint64_t bytes, void **d_ptr, NrbIpcHandle *handle) {
+  if (!d_ptr || !handle || bytes == 0) return fail(NRB_ERR_INVALID_ARG, "ipc_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(NrbIpcHandle), "NrbIpcHandle must hold a cudaIpcMemHandle_t");
+  CU(cudaSetDevice(device));
+  void *p = nullptr;
+  CU(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(NRB_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  CU(cudaMemset(p, 0, bytes));
+  std::memcpy(handle->bytes, &h, sizeof(h));
+  *d_ptr = p;
+  return NRB_OK;
+}
+
+int nrb_ipc_open(int device, const NrbIpcHandle *handle, void **d_ptr) {
+  if (!d_ptr || !handle) return fail(NRB_ERR_INVALID_ARG, "ipc_open: bad arguments");
+  CU(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle->bytes, sizeof(h));
+  void *p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(NRB_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+  }
+  *d_ptr = p;
+  return NRB_OK;
+}
+
+int nrb_ipc_close(int device, void *d_ptr) {
+  if (!d_ptr) return NRB_OK;
+  CU(cudaSetDevice(device));
+  CU(cudaIpcCloseMemHandle(d_ptr));
+  return NRB_OK;
+}
+
+int nrb_ipc_free(int device, void *d_ptr) {
+  if (!d_ptr) return NRB_OK;
+  CU(cudaSetDevice(device));
+  CU(cudaFree(d_ptr));
+  return NRB_OK;
 }
 
 uint32_t nrb_tile_count(uint32_t width, uint32_t height) {

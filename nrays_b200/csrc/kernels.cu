@@ -341,6 +341,10 @@ NRB_DI void trav_run(const SceneView &sc, LaneTrav &s, int *lm, bool any, int mi
 // Hands queue entries to the idle lanes of a persistent warp.  The warp keeps a private pool
 // [pool_base, pool_base + pool_left) of entries taken from the global cursor 32 * kFetchPackets at a time
 // (one atomic per chunk); idle lanes get consecutive indices.
+// Entries a warp takes per cursor atomic: kFetchPackets packets while the queue gives every resident warp several
+// fetches, single packets below that so the last fetches of a small launch balance better (tile-sharded frames).
+NRB_DI uint32_t fetch_chunk(uint32_t count) { return count >= kSmallQueue ? 32u * kFetchPackets : 32u; }
+
 struct RayPool {  // one per warp, in shared memory (keeps three registers out of the traversal loop)
   uint32_t base, left, more;  // more: the global cursor may still have entries
 };
@@ -354,7 +358,7 @@ NRB_DI void pool_reset(RayPool *pool) {
 
 NRB_DI bool pool_empty(const RayPool *pool) { return pool->more == 0u && pool->left == 0u; }
 
-NRB_DI uint32_t pool_assign(RayPool *pool, bool idle, uint32_t *cursor, uint32_t count) {
+NRB_DI uint32_t pool_assign(RayPool *pool, bool idle, uint32_t *cursor, uint32_t count, uint32_t chunk) {
   const uint32_t lane = lane_id();
   const uint32_t mask = __ballot_sync(0xFFFFFFFFu, idle);
   uint32_t mine = kNoRay;
@@ -367,12 +371,12 @@ NRB_DI uint32_t pool_assign(RayPool *pool, bool idle, uint32_t *cursor, uint32_t
   base += take, left -= take;
   if (take < need && more) {
     uint32_t nb = 0;
-    if (lane == 0) nb = atomicAdd(cursor, 32u * kFetchPackets);
+    if (lane == 0) nb = atomicAdd(cursor, chunk);
     nb = __shfl_sync(0xFFFFFFFFu, nb, 0);
     if (nb >= count) {
       more = 0u;
     } else {
-      base = nb, left = min(32u * kFetchPackets, count - nb);
+      base = nb, left = min(chunk, count - nb);
       const uint32_t take2 = min(need - take, left);
       if (idle && rank >= take && rank < take + take2) mine = base + (rank - take);
       base += take2, left -= take2;
@@ -639,7 +643,7 @@ NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *acc
   uint32_t idx = 0;
   int cand = -1;
   while (true) {
-    const uint32_t mine = pool_assign(pool, !active, &wc_shadow->fetch_shadow, count);
+    const uint32_t mine = pool_assign(pool, !active, &wc_shadow->fetch_shadow, count, fetch_chunk(count));
     if (mine != kNoRay) {
       idx = mine;
       bool occluded = false;
@@ -671,7 +675,7 @@ NRB_DI void drain_closest(const SceneView &sc, const FrameParams &fp, const RayQ
   bool active = false;
   uint32_t idx = 0;
   while (true) {
-    const uint32_t mine = pool_assign(pool, !active, &wc_closest->fetch_closest, count);
+    const uint32_t mine = pool_assign(pool, !active, &wc_closest->fetch_closest, count, fetch_chunk(count));
     if (mine != kNoRay) {
       idx = mine;
       bool valid = true;
@@ -1120,6 +1124,34 @@ __global__ void resolve_rgb8_kernel(const float4 *accum, uint32_t n, float spp, 
   }
 }
 
+// K5 + K6 fused for the multi-GPU path: this rank's packed tile accumulators are resolved (/ spp) straight into the
+// ROW-MAJOR image `out_rgb`, which may live on another GPU (peer / IPC-mapped memory over NVLink): the finished
+// pixels cross the link once, as 48-byte stores of four pixels, and nothing is gathered or un-tiled afterwards.
+__global__ void resolve_tiles_to_image_kernel(const float4 *accum, FrameParams fp, float inv_spp, float *out_rgb) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread = four pixels of one tile row
+  if (t >= fp.n_local_tiles * (NRB_TILE * NRB_TILE / 4u)) return;
+  const uint32_t lt = t / (NRB_TILE * NRB_TILE / 4u), r = t % (NRB_TILE * NRB_TILE / 4u);
+  const uint32_t row = r / (NRB_TILE / 4u), x4 = (r % (NRB_TILE / 4u)) * 4u;
+  const uint32_t tile = fp.tile_first + lt * fp.tile_stride;
+  const uint32_t ty = fdiv(tile, fp.div_tiles_x), tx = tile - ty * fp.tiles_x;
+  const uint32_t y = ty * NRB_TILE + row, x = tx * NRB_TILE + x4;
+  if (y >= fp.height || x >= fp.width) return;
+  const float4 *src = accum + (size_t)lt * (NRB_TILE * NRB_TILE) + row * NRB_TILE + x4;
+  float *dst = out_rgb + 3u * ((size_t)y * fp.width + x);
+  if (x + 3u < fp.width && (fp.width & 3u) == 0u) {
+    const float4 a = src[0], b = src[1], c = src[2], d = src[3];
+    float4 *d4 = reinterpret_cast<float4 *>(dst);  // 12 * (y * W + x) bytes: 16-byte aligned when W % 4 == 0 and x % 4 == 0
+    d4[0] = make_float4(a.x * inv_spp, a.y * inv_spp, a.z * inv_spp, b.x * inv_spp);
+    d4[1] = make_float4(b.y * inv_spp, b.z * inv_spp, c.x * inv_spp, c.y * inv_spp);
+    d4[2] = make_float4(c.z * inv_spp, d.x * inv_spp, d.y * inv_spp, d.z * inv_spp);
+  } else {
+    for (uint32_t k = 0; k < 4u && x + k < fp.width; ++k) {
+      const float4 a = src[k];
+      dst[3 * k + 0] = a.x * inv_spp, dst[3 * k + 1] = a.y * inv_spp, dst[3 * k + 2] = a.z * inv_spp;
+    }
+  }
+}
+
 // K6 — packed tiles of n_ranks ranks (rank r owns tiles r, r+n_ranks, ...) -> row-major image
 __global__ void untile_kernel(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width,
                               uint32_t height, uint32_t tiles_x, float *out_rgb) {
@@ -1200,6 +1232,12 @@ void launch_resolve(const float4 *accum, uint32_t n, uint32_t spp, float *out_rg
 void launch_resolve_rgb8(const float4 *accum, uint32_t n, uint32_t spp, uint8_t *out, cudaStream_t st) {
   if (!n) return;
   resolve_rgb8_kernel<<<(n + 255) / 256, 256, 0, st>>>(accum, n, (float)spp, out);
+}
+
+void launch_resolve_tiles_to_image(const float4 *accum, const FrameParams &fp, float *out_rgb, cudaStream_t st) {
+  const uint32_t n = fp.n_local_tiles * (NRB_TILE * NRB_TILE / 4u);
+  if (!n) return;
+  resolve_tiles_to_image_kernel<<<(n + 255) / 256, 256, 0, st>>>(accum, fp, 1.0f / (float)fp.spp, out_rgb);
 }
 
 void launch_untile(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width, uint32_t height,

@@ -14,6 +14,10 @@ constexpr int kTraceBlock = 128;
 #ifndef NRB_NODE_LOADS
 #define NRB_NODE_LOADS 1
 #endif
+#ifndef NRB_SMALL_QUEUE
+#define NRB_SMALL_QUEUE (3u << 20)
+#endif
+constexpr unsigned kSmallQueue = NRB_SMALL_QUEUE;  // queues shorter than this are fetched one 32-ray packet at a time
 constexpr int kFetchPackets = NRB_FETCH_PACKETS;  // 32-ray packets a warp takes per cursor atomic
 constexpr int kTraceMinBlocks = NRB_TRACE_MIN_BLOCKS;  // resident CTAs / SM the trace kernel is compiled for
 #ifndef NRB_TAIL_MIN_BLOCKS
@@ -39,6 +43,7 @@ void launch_tail(const SceneView &sc, bool has_shapes, const FrameParams &fp, Ra
 int shade_blocks_per_sm(bool has_shapes);
 void launch_resolve(const float4 *accum, uint32_t n, uint32_t spp, float *out_rgb, cudaStream_t st);
 void launch_resolve_rgb8(const float4 *accum, uint32_t n, uint32_t spp, uint8_t *out, cudaStream_t st);
+void launch_resolve_tiles_to_image(const float4 *accum, const FrameParams &fp, float *out_rgb, cudaStream_t st);
 void launch_untile(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width, uint32_t height,
                    float *out_rgb, cudaStream_t st);
 int trace_blocks_per_sm(bool has_shapes);

@@ -105,3 +105,82 @@ def use_stream(scene, stream_ptr):
     from . import _lib
 
     _lib.check(_lib.load().nrb_scene_set_stream(scene.handle, C.c_void_p(stream_ptr or 0)))
+
+
+# ---- fused exchange: every rank resolves its tiles straight into the owner's image over NVLink --------------
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier so torch can view library-owned device memory."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerImage:
+    """Row-major W*H*3 float image in the memory of rank `owner`, mapped into every rank of the node with CUDA IPC.
+
+    Replaces gather + un-tile: `render_tiles_to_image` makes each rank's resolve kernel store its finished pixels
+    into this image directly (peer stores over NVLink / NVSwitch), so each pixel crosses the fabric once and only
+    the owner receives anything; `sync()` (one 4-byte all-reduce on the render stream) orders the ranks before the
+    owner reads.  Collective constructor: call it on every rank of the default process group.
+    """
+
+    def __init__(self, width, height, rank, world, device, owner=0):
+        import torch
+        import torch.distributed as td
+
+        from . import _lib
+
+        self.lib, self.rank, self.world, self.device, self.owner = _lib.load(), rank, world, int(device), owner
+        self.n_floats = width * height * 3
+        self.ptr = C.c_void_p()
+        handle = A.NrbIpcHandle()
+        ok = True
+        if rank == owner:
+            ok = self.lib.nrb_ipc_alloc(self.device, self.n_floats * 4, C.byref(self.ptr), C.byref(handle)) == A.NRB_OK
+        hb = torch.tensor(list(bytes(handle.bytes)) + [1 if ok else 0], dtype=torch.uint8, device="cuda:%d" % self.device)
+        td.broadcast(hb, src=owner)
+        raw = hb.cpu().numpy().tobytes()
+        if not raw[64]:
+            raise RuntimeError("PeerImage: the owner could not allocate / export the image")
+        if rank != owner:
+            C.memmove(handle.bytes, raw[:64], 64)
+            ok = self.lib.nrb_ipc_open(self.device, C.byref(handle), C.byref(self.ptr)) == A.NRB_OK
+        # every rank must know whether every rank has the mapping
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda:%d" % self.device)
+        td.all_reduce(flag, op=td.ReduceOp.MIN)
+        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.device)
+        if int(flag.item()) == 0:
+            self.close()
+            raise RuntimeError("PeerImage: CUDA IPC mapping failed on some rank: " + self.lib.nrb_last_error().decode("utf-8", "replace"))
+
+    def tensor(self):
+        """torch view of the image (owner only)."""
+        import torch
+
+        assert self.rank == self.owner
+        return torch.as_tensor(_DevArray(self.ptr.value, self.n_floats), device="cuda:%d" % self.device)
+
+    def sync(self):
+        """Orders all ranks' peer stores before whatever the owner enqueues next on its current stream."""
+        import torch.distributed as td
+
+        td.all_reduce(self._flag)
+
+    def close(self):
+        if self.ptr:
+            if self.rank == self.owner:
+                self.lib.nrb_ipc_free(self.device, self.ptr)
+            else:
+                self.lib.nrb_ipc_close(self.device, self.ptr)
+            self.ptr = C.c_void_p()
+
+
+def render_tiles_to_image(scene, cam, rank, world, image_ptr):
+    """Render this rank's tiles and resolve them into the row-major image at `image_ptr` (local or peer memory)."""
+    from . import _lib
+
+    ts = A.NrbTileSet(rank, world)
+    stats = A.NrbStats()
+    ptr = image_ptr if isinstance(image_ptr, C.c_void_p) else C.c_void_p(int(image_ptr))
+    _lib.check(_lib.load().nrb_render_tiles_to_image(scene.handle, C.byref(cam), C.byref(ts), ptr, C.byref(stats)))
+    return stats

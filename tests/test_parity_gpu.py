@@ -218,6 +218,36 @@ def test_tile_sharded_render_equals_full_frame(gpu):
     scene.close()
 
 
+@pytest.mark.parametrize("w,h,world", [(200, 120, 8), (203, 77, 3), (16, 16, 2)])
+def test_tiles_resolved_straight_into_the_image(gpu, w, h, world):
+    """The fused exchange (nrb_render_tiles_to_image): every virtual rank writes only its own pixels of ONE row-major
+    image; after all ranks the image is the unsharded frame.  (203 wide: the scalar store path; ragged tiles.)"""
+    import torch
+
+    from nrays_b200 import dist
+
+    scene, camd, cfg = configs.build("C3", target_tris=30000, lod=4)
+    cam = make_camera(w, h, 2, 1.0, camd.eye, camd.projection((w, h)), seed=6)
+    full = torch.empty(h * w * 3, dtype=torch.float32, device="cuda")
+    dist.render_device(scene, cam, full)
+    img = torch.full((h * w * 3,), -7.0, dtype=torch.float32, device="cuda")
+    owned = np.zeros((h, w), bool)
+    for r in range(world):
+        before = img.clone()
+        dist.render_tiles_to_image(scene, cam, r, world, img.data_ptr())
+        changed = (img != before).reshape(h, w, 3).any(dim=2).cpu().numpy()
+        mine = np.zeros((h, w), bool)
+        tx, _ty = dist.tile_grid(w, h)
+        for t in dist.local_tiles(w, h, r, world):
+            y0, x0 = (t // tx) * 16, (t % tx) * 16
+            mine[y0:y0 + 16, x0:x0 + 16] = True
+        assert not (changed & ~mine).any(), "rank %d wrote pixels it does not own" % r
+        owned |= mine
+    assert owned.all()
+    np.testing.assert_allclose(img.cpu().numpy(), full.cpu().numpy(), rtol=0, atol=2e-6)
+    scene.close()
+
+
 # ---- driver paths that the default sizes never reach -------------------------------------------------
 class _Env:
     def __init__(self, **kv):
