@@ -79,3 +79,49 @@ def test_planes_stay_outside_the_bvh():
              node(Ball(1.0), NormalMaterial())]
     rc, info, err = validate(Scene(nodes, [], upload=False).flat)
     assert rc == A.NRB_OK and info.planes == 2 and info.shapes == 3 and info.transparent_candidates == 0 and info.bvh_nodes == 0
+
+
+def test_fast_division_by_frame_constants_is_exact(tmp_path):
+    """The kernels divide by spp / tiles_x / width with a precomputed 64-bit reciprocal (device_types.cuh: FastDiv).
+    The same struct and formula, compiled for the host, must equal `/` for every divisor the frame can produce."""
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = "/usr/local/cuda/include"
+    if not (shutil.which("g++") and os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h"))):
+        pytest.skip("needs g++ and the CUDA headers")
+    src = tmp_path / "fd.cpp"
+    src.write_text(r'''
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "device_types.cuh"
+using namespace nrb;
+static uint32_t fdiv(uint32_t n, const FastDiv &f) {  // == device_math.cuh: fdiv
+  if (f.d == 1u) return n;
+  unsigned long long lo = (unsigned long long)f.mul_lo * n;
+  unsigned long long hi = (unsigned long long)f.mul_hi * n + (lo >> 32);
+  return (uint32_t)(hi >> 32);
+}
+int main() {
+  unsigned long long bad = 0;
+  uint32_t ds[] = {1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 120, 121, 240, 255, 256, 1000, 1080, 1920, 3840, 65535, 65536, 1u << 31, 0x7fffffffu, 0xffffffffu};
+  for (uint32_t d : ds) {
+    FastDiv f = make_fastdiv(d);
+    for (unsigned long long n = 0; n < (1ull << 32); n += 65521) bad += fdiv((uint32_t)n, f) != (uint32_t)n / d;
+    uint32_t edge[] = {0u, 1u, d - 1, d, d + 1, 2 * d - 1, 2 * d, 0xfffffffeu, 0xffffffffu, 0xffffffffu - d, 0xffffffffu / d * d, 0xffffffffu / d * d - 1};
+    for (uint32_t n : edge) bad += fdiv(n, f) != n / d;
+  }
+  for (uint32_t d = 1; d < 5000; ++d) {
+    FastDiv f = make_fastdiv(d);
+    for (uint32_t n = 0; n < 300000; n += 7) bad += fdiv(n, f) != n / d;
+    bad += fdiv(0xffffffffu, f) != 0xffffffffu / d;
+  }
+  printf("%llu\n", bad);
+  return bad != 0;
+}
+''')
+    exe = tmp_path / "fd"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", cuda_inc, "-I", os.path.join(root, "nrays_b200", "csrc"), "-o", str(exe), str(src)])
+    assert subprocess.check_output([str(exe)]).strip() == b"0"
