@@ -6,7 +6,9 @@
 //   K4 shade_kernel           src/scene.rs:168-252, src/phong_material.rs:72-151, src/light.rs:56-63,
 //                             src/texture2d.rs:207-256, normal/uv materials
 //   K5 resolve_kernel         src/scene.rs:94 (tot_c / spp) [+ src/image.rs:64-77 RGB8 quantisation]
-//   K6 untile_kernel          (multi-GPU) packed 16x16 tiles -> row-major image
+//   K5+K6 resolve_tiles_to_image_kernel   (multi-GPU) this rank's tiles / spp stored straight into the owner's row-major
+//                             image, local or peer memory over NVLink: the path's one exchange, fused into the resolve
+//   K6 untile_kernel          (multi-GPU, all-gather fallback) packed 16x16 tiles -> row-major image
 //
 // The reference recursion `trace` is linear in its reflection / refraction children, so each ray
 // carries a scalar weight and every hit / miss / unoccluded light sample adds its weighted colour
