@@ -733,15 +733,18 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   const uint32_t S_total = (uint32_t)S.view.shadow_samples;
   const uint64_t tail_threshold = env_size("NRB_TAIL_RAYS", 4u << 20);
   const uint32_t tail_min_wave = (uint32_t)env_size("NRB_TAIL_MIN_WAVE", 2);
-  // Dynamic fetch of the trace kernel: a warp pauses to refill its idle lanes once fewer than this many lanes are
-  // still traversing (0 = only when all 32 are done).  Measured (profiles/README.md): on the coherent headline
-  // config every non-zero setting loses 8-25 % (the refill rounds cost more than the idle lanes), on the incoherent
-  // hairball 20 lanes for shadow rays gains ~7 %; the default keeps whole packets.
+  // Trace-kernel knobs (profiles/README.md has the measurements).  Dynamic fetch — a warp pauses to refill its idle lanes
+  // once fewer than N lanes are still traversing — loses 8-25 % on coherent frames (a refill round costs more than
+  // the idle lanes) and gains ~7 % where neighbouring rays diverge; single-packet fetches balance such frames better
+  // (-4 %).  "Fine geometry" = more triangles than half the pixels, i.e. triangles smaller than the pixel grid
+  // (hairball: 2.88 M triangles behind 2.07 M pixels): there the secondary / shadow queues use both.
   // opaque any-hit phase of shadow rays walked from the light end (rays of one point light leave together)
   const int reverse_shadow = (int)env_size("NRB_REVERSE_SHADOW", 1);
+  const bool fine_geometry = S.n_tris > (uint64_t)fp.width * fp.height / 2;
   const int refill_primary = (int)env_size("NRB_REFILL_PRIMARY", 0);
-  const int refill_rays = (int)env_size("NRB_REFILL_RAYS", 0);
-  const int refill_shadow = (int)env_size("NRB_REFILL_SHADOW", 0);
+  const int refill_rays = (int)env_size("NRB_REFILL_RAYS", fine_geometry ? 20 : 0);
+  const int refill_shadow = (int)env_size("NRB_REFILL_SHADOW", fine_geometry ? 20 : 0);
+  const uint32_t small_queue = (uint32_t)env_size("NRB_SMALL_QUEUE", fine_geometry ? 0xFFFFFFFFu : kSmallQueue);
   uint64_t primary = 0;
 
   const size_t wc_len = (size_t)fp.max_depth + 3;
@@ -777,7 +780,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
       cudaEvent_t e0 = get_event(S, ev_used), e1 = get_event(S, ev_used);
       CU(cudaEventRecord(e0, st));
       launch_trace(S.view, S.has_shapes, fp, primary, q, S.d_hits.as<float4>(), wcc, slot_lo, n_slots, sq, accum, wcs,
-                   primary ? refill_primary : refill_rays, refill_shadow, reverse_shadow, S.grid_trace, st);
+                   TraceOpts{primary ? refill_primary : refill_rays, refill_shadow, reverse_shadow, small_queue}, S.grid_trace, st);
       CU(cudaEventRecord(e1, st));
       trace_spans.emplace_back(e0, e1);
       ++launches;

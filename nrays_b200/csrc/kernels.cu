@@ -106,7 +106,8 @@ NRB_DI NodeRec load_node(const SceneView &sc, int node) {
   const BvhNode *np = sc.nodes + node;
 #if NRB_NODE_LOADS == 1
   // two 256-bit loads (LDG.E.256, sm_100+) fetch the whole record; the child codes arrive with the boxes
-  int pad0, pad1;
+  int pad0, pad1;  // the record's two unused words
+  (void)pad0, (void)pad1;
   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(r.n0.x), "=f"(r.n0.y), "=f"(r.n0.z), "=f"(r.n0.w), "=f"(r.n1.x), "=f"(r.n1.y), "=f"(r.n1.z), "=f"(r.n1.w)
                : "l"(np));
@@ -345,7 +346,7 @@ NRB_DI void trav_run(const SceneView &sc, LaneTrav &s, int *lm, bool any, int mi
 // (one atomic per chunk); idle lanes get consecutive indices.
 // Entries a warp takes per cursor atomic: kFetchPackets packets while the queue gives every resident warp several
 // fetches, single packets below that so the last fetches of a small launch balance better (tile-sharded frames).
-NRB_DI uint32_t fetch_chunk(uint32_t count) { return count >= kSmallQueue ? 32u * kFetchPackets : 32u; }
+NRB_DI uint32_t fetch_chunk(uint32_t count, uint32_t small_queue) { return count >= small_queue ? 32u * kFetchPackets : 32u; }
 
 struct RayPool {  // one per warp, in shared memory (keeps three registers out of the traversal loop)
   uint32_t base, left, more;  // more: the global cursor may still have entries
@@ -636,7 +637,7 @@ NRB_DI bool shadow_planes(const SceneView &sc, const ShadowQueue &sq, uint32_t i
 
 template <bool HAS_SHAPES>
 NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *accum, WaveCounters *wc_shadow, int min_active,
-                         bool reverse, RayPool *pool, int *lm) {
+                         bool reverse, uint32_t small_queue, RayPool *pool, int *lm) {
   const uint32_t count = min(wc_shadow->n_shadow, sq.capacity);
   LaneTrav s;
   s.node = kEmpty;
@@ -645,7 +646,7 @@ NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *acc
   uint32_t idx = 0;
   int cand = -1;
   while (true) {
-    const uint32_t mine = pool_assign(pool, !active, &wc_shadow->fetch_shadow, count, fetch_chunk(count));
+    const uint32_t mine = pool_assign(pool, !active, &wc_shadow->fetch_shadow, count, fetch_chunk(count, small_queue));
     if (mine != kNoRay) {
       idx = mine;
       bool occluded = false;
@@ -668,8 +669,8 @@ NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *acc
 
 template <bool HAS_SHAPES, bool PRIMARY>
 NRB_DI void drain_closest(const SceneView &sc, const FrameParams &fp, const RayQueue &q, float4 *hits,
-                          WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, int min_active, RayPool *pool,
-                          int *lm) {
+                          WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, int min_active, uint32_t small_queue,
+                          RayPool *pool, int *lm) {
   const uint32_t count = PRIMARY ? n_slots : wc_closest->n_rays;
   LaneTrav s;
   s.node = kEmpty;
@@ -677,7 +678,7 @@ NRB_DI void drain_closest(const SceneView &sc, const FrameParams &fp, const RayQ
   bool active = false;
   uint32_t idx = 0;
   while (true) {
-    const uint32_t mine = pool_assign(pool, !active, &wc_closest->fetch_closest, count, fetch_chunk(count));
+    const uint32_t mine = pool_assign(pool, !active, &wc_closest->fetch_closest, count, fetch_chunk(count, small_queue));
     if (mine != kNoRay) {
       idx = mine;
       bool valid = true;
@@ -730,17 +731,18 @@ NRB_DI void drain_closest(const SceneView &sc, const FrameParams &fp, const RayQ
 template <bool HAS_SHAPES, bool PRIMARY>
 __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 6 : kTraceMinBlocks)
     trace_kernel(SceneView sc, FrameParams fp, RayQueue q, float4 *hits, WaveCounters *wc_closest, uint32_t slot_lo,
-                 uint32_t n_slots, ShadowQueue sq, float4 *accum, WaveCounters *wc_shadow, int min_active_closest,
-                 int min_active_shadow, int reverse_shadow) {
+                 uint32_t n_slots, ShadowQueue sq, float4 *accum, WaveCounters *wc_shadow, TraceOpts opts) {
   __shared__ RayPool pools[kTraceBlock / 32];
   RayPool *pool = &pools[threadIdx.x >> 5];
   int lm[kLmSize];  // the lane's ray, best hit and traversal stack (see LaneTrav)
   const bool closest_first = blockIdx.x & 1u;
   for (int phase = 0; phase < 2; ++phase) {
     if ((phase == 0) == closest_first) {
-      if (wc_closest) drain_closest<HAS_SHAPES, PRIMARY>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, min_active_closest, pool, lm);
+      if (wc_closest)
+        drain_closest<HAS_SHAPES, PRIMARY>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, opts.min_active_closest, opts.small_queue, pool, lm);
     } else {
-      if (wc_shadow) drain_shadow<HAS_SHAPES>(sc, sq, accum, wc_shadow, min_active_shadow, reverse_shadow != 0, pool, lm);
+      if (wc_shadow)
+        drain_shadow<HAS_SHAPES>(sc, sq, accum, wc_shadow, opts.min_active_shadow, opts.reverse_shadow != 0, opts.small_queue, pool, lm);
     }
   }
 }
@@ -1173,12 +1175,11 @@ __global__ void untile_kernel(const float *gathered, uint32_t n_ranks, uint32_t 
 // ---------------------------------------------------------------------------------------------
 void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue q, float4 *hits,
                   WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, ShadowQueue sq, float4 *accum,
-                  WaveCounters *wc_shadow, int min_active_closest, int min_active_shadow, int reverse_shadow, int grid,
-                  cudaStream_t st) {
+                  WaveCounters *wc_shadow, TraceOpts opts, int grid, cudaStream_t st) {
   if (!wc_closest && !wc_shadow) return;
 #define NRB_LAUNCH_TRACE(HS, PR)                                                                                       \
   trace_kernel<HS, PR><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow, \
-                                                     min_active_closest, min_active_shadow, reverse_shadow)
+                                                     opts)
   if (has_shapes) {
     if (primary) NRB_LAUNCH_TRACE(true, true); else NRB_LAUNCH_TRACE(true, false);
   } else {

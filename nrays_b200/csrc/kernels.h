@@ -17,7 +17,7 @@ constexpr int kTraceBlock = 128;
 #ifndef NRB_SMALL_QUEUE
 #define NRB_SMALL_QUEUE (3u << 20)
 #endif
-constexpr unsigned kSmallQueue = NRB_SMALL_QUEUE;  // queues shorter than this are fetched one 32-ray packet at a time
+constexpr unsigned kSmallQueue = NRB_SMALL_QUEUE;  // default TraceOpts.small_queue
 constexpr int kFetchPackets = NRB_FETCH_PACKETS;  // 32-ray packets a warp takes per cursor atomic
 constexpr int kTraceMinBlocks = NRB_TRACE_MIN_BLOCKS;  // resident CTAs / SM the trace kernel is compiled for
 #ifndef NRB_TAIL_MIN_BLOCKS
@@ -30,10 +30,16 @@ constexpr int kShadeBlock = 128;
 #endif
 constexpr int kShadeMinBlocks = NRB_SHADE_MIN_BLOCKS;  // 6: shade capped at 80 registers -> 768 resident threads / SM
 
+// Run-time knobs of one trace launch.
+struct TraceOpts {
+  int min_active_closest;  // dynamic fetch: a warp refills its idle lanes once fewer than this many are traversing (0: never early)
+  int min_active_shadow;
+  int reverse_shadow;      // opaque any-hit phase of shadow rays walked from the light end
+  uint32_t small_queue;    // queues shorter than this are fetched one 32-ray packet at a time (else kFetchPackets packets)
+};
 void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue q, float4 *hits,
                   WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, ShadowQueue sq, float4 *accum,
-                  WaveCounters *wc_shadow, int min_active_closest, int min_active_shadow, int reverse_shadow, int grid,
-                  cudaStream_t st);
+                  WaveCounters *wc_shadow, TraceOpts opts, int grid, cudaStream_t st);
 void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue qin,
                   const float4 *hits, WaveCounters *wc, uint32_t slot_lo, uint32_t n_slots, uint32_t lo, uint32_t hi,
                   RayQueue qout, ShadowQueue sq, Counters *ctr, float4 *accum, int grid, cudaStream_t st);
