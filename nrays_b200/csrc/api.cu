@@ -303,6 +303,8 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
         int node_id = (int)i;
         std::memcpy(&tr.t0.w, &node_id, 4);
         tr.t1 = make_float4((float)(w[1][0] - w[0][0]), (float)(w[1][1] - w[0][1]), (float)(w[1][2] - w[0][2]), 0.0f);
+        int material_id = (int)n.material;  // copy of NodeInfo.material: shade fetches the material without waiting for NodeInfo
+        std::memcpy(&tr.t1.w, &material_id, 4);
         tr.t2 = make_float4((float)(w[2][0] - w[0][0]), (float)(w[2][1] - w[0][1]), (float)(w[2][2] - w[0][2]), 0.0f);
         tris_in[t_out] = tr;
         uvs_in[t_out] = uv;

@@ -42,7 +42,7 @@ struct __align__(16) Tri {
   float4 t0, t1, t2;
 };
 // Per-triangle vertex uvs, fetched only by the shade / shadow-filter code: 24 bytes.
-struct TriUV {
+struct __align__(8) TriUV {  // three 64-bit loads
   float u0, v0, u1, v1, u2, v2;
 };
 
