@@ -342,6 +342,9 @@ def run_ours(args, rank, local_rank, world):
             "bytes_per_launch": bytes_k / max(1, l_k), "ms_per_launch": ms_k / max(1, l_k),
             "kernel_share_of_step": ms_k / ms_dev if ms_dev > 0 else None,
             "limiter_ncu": ncu_note,   # what actually bounds the kernel (ncu, profiles/): not HBM
+            # BASELINE's "HBM GB/s vs peak": ncu DRAM bytes per launch over the live launch time
+            "traffic_gbs": (traffic / (ms_k / max(1, l_k) * 1e-3) / 1e9) if (traffic and ms_k > 0) else None,
+            "traffic_frac": (traffic / (ms_k / max(1, l_k) * 1e-3) / 1e9 / peak) if (traffic and ms_k > 0) else None,
             "frame": {"algorithmic_bytes_per_step": frame_bytes / len(stats_dev),
                       "achieved": frame_bytes / (ms_dev_max * 1e-3) / 1e9, "peak": peak * world,
                       "frac": frame_bytes / (ms_dev_max * 1e-3) / 1e9 / (peak * world)},
