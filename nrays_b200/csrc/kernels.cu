@@ -546,12 +546,6 @@ NRB_DI void shadow_query(const SceneView &sc, V3 o, V3 d, float tmax, uint32_t p
   if (!occluded) accum_add(accum, pix, cmul(contrib, filter));
 }
 
-template <bool HAS_SHAPES>
-NRB_DI void shadow_ray(const SceneView &sc, const ShadowQueue &q, uint32_t i, float4 *accum) {
-  float4 a = q.a[i], b = q.b[i], c = q.c[i];
-  shadow_query<HAS_SHAPES>(sc, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), a.w, __float_as_uint(b.w), mk(c.x, c.y, c.z), accum);
-}
-
 // ---------------------------------------------------------------------------------------------
 // The persistent trace kernel: ONE launch per wave drains the shadow queue of the previous wave
 // (any-hit + transparent filter, adds into the pixel accumulator) and the ray queue of this wave
