@@ -129,6 +129,9 @@ def main():
             m6432 = image_metrics(ref, ref32)
             note = " | vs f32 twin: frac_over=%.4f rays=%d counts_%s | f64 vs f32 oracle: frac_over=%.4f" % (
                 m32["frac_over"], ost32.rays_reference, "ok" if c32 else "DIFFER", m6432["frac_over"])
+            keys = ("rays_primary", "rays_reflect", "rays_refract", "rays_shadow", "paths_truncated")
+            note += " | classes dev/f64/f32: " + " ".join("%s=%d/%d/%d" % (k[5:] if k.startswith("rays_") else k, getattr(st, k), getattr(ost, k),
+                                                                            getattr(ost32, k)) for k in keys)
             if m32["frac_over"] <= 5e-3 and c32:
                 ok = True
                 note += " -> precision-chaotic, agrees with the twin"
