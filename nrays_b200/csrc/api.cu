@@ -569,6 +569,26 @@ std::vector<BvhNode> to_centre_half(const std::vector<BvhNode> &in) {
   return out;
 }
 
+// The device boxes (centre -+ half extent, evaluated in f32 as the kernel sees them) must contain the builder's boxes.
+int check_device_nodes(const HostScene &H, std::string &why) {
+  const std::vector<BvhNode> dev = to_centre_half(H.nodes);
+  for (size_t i = 0; i < H.nodes.size(); ++i) {
+    const BvhNode &n = H.nodes[i], &d = dev[i];
+    const float lo[2][3] = {{n.n0.x, n.n0.z, n.n2.x}, {n.n1.x, n.n1.z, n.n2.z}};
+    const float hi[2][3] = {{n.n0.y, n.n0.w, n.n2.y}, {n.n1.y, n.n1.w, n.n2.w}};
+    const float c[2][3] = {{d.n0.x, d.n0.y, d.n0.z}, {d.n0.w, d.n1.x, d.n1.y}};
+    const float h[2][3] = {{d.n1.z, d.n1.w, d.n2.x}, {d.n2.y, d.n2.z, d.n2.w}};
+    for (int b = 0; b < 2; ++b)
+      for (int k = 0; k < 3; ++k) {
+        const float l = std::max(lo[b][k], -1.0e30f), u = std::min(hi[b][k], 1.0e30f);
+        if (!(c[b][k] - h[b][k] <= l) || !(c[b][k] + h[b][k] >= u) || !(h[b][k] >= 0.0f))
+          return why = "device box (centre / half extent) does not contain the builder's box", 1;
+      }
+    if (d.n3.x != n.n3.x || d.n3.y != n.n3.y) return why = "device node lost its child codes", 1;
+  }
+  return 0;
+}
+
 int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
   CU(upload(S.d_nodes, to_centre_half(H.nodes)));
   CU(upload(S.d_tris, H.tris));
@@ -1048,7 +1068,7 @@ int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOp
   if (rc) return rc;
   if (getenv("NRB_CHECK_BVH")) {  // structural self-check of whatever builder ran (tests)
     std::string why;
-    if (check_bvh(H, why)) return fail(NRB_ERR_CUDA + 100, "internal BVH invariant violated: " + why);
+    if (check_bvh(H, why) || check_device_nodes(H, why)) return fail(NRB_ERR_CUDA + 100, "internal BVH invariant violated: " + why);
   }
   rc = upload_scene(*desc, H, *S);
   if (rc) return rc;
@@ -1086,7 +1106,7 @@ int nrb_scene_validate(const NrbSceneDesc *desc, NrbBuildInfo *info) {
   if (rc) return rc;
   double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   std::string why;
-  if (check_bvh(H, why)) return fail(NRB_ERR_CUDA + 100, "internal BVH invariant violated: " + why);
+  if (check_bvh(H, why) || check_device_nodes(H, why)) return fail(NRB_ERR_CUDA + 100, "internal BVH invariant violated: " + why);
   if (const char *path = getenv("NRB_DUMP_BVH")) {  // builder experiments (scripts/bvh_sim.cpp): nodes + triangles as built
     if (FILE *f = fopen(path, "wb")) {
       uint64_t hdr[4] = {H.nodes.size(), H.tris.size(), (uint64_t)(uint32_t)H.root_all, (uint64_t)(uint32_t)H.root_opaque};

@@ -1,6 +1,7 @@
 """Host half of Scene::new through the C-ABI (nrb_scene_validate): table validation and the BVH builder's
 structural invariants (checked inside the library: every triangle in exactly one leaf, child boxes inside
-their parent's, every node reachable once).  Runs without a GPU."""
+their parent's, every node reachable once, and the device copy of every box — centre + half extent, rounded
+up — contains the builder's box).  Runs without a GPU."""
 import ctypes as C
 import os
 
