@@ -75,7 +75,7 @@ typedef struct NrbNodeDesc {
   float refl_atenuation;    /* SceneNode.refl_atenuation (sic) */
   float alpha;              /* SceneNode.alpha */
   int32_t solid;            /* SceneNode.solid (bool) */
-  int32_t nmap_texture;     /* SceneNode.nmap: texture index or -1 (loader never sets it: loader3d.rs:553) */
+  int32_t nmap_texture;     /* SceneNode.nmap (depth shift, src/scene_node.rs:60-70): texture index or -1; <= 32 such nodes */
   int32_t _pad;
   /* TRIMESH only: triangles [first_index/3, first_index/3 + tri_count) of `indices`,
    * each index relative to `vertex_base` in positions/uvs (TriMesh::new(coords, faces, Some(uvs))). */

@@ -80,9 +80,10 @@ struct NrbScene {
   int sm_count = 148;
   // scene tables
   DevBuf d_nodes, d_tris, d_tri_uvs, d_shapes, d_node_info, d_materials, d_textures, d_texels, d_lights, d_planes,
-      d_candidates;
+      d_candidates, d_nmaps;
   SceneView view{};
   bool has_shapes = false;
+  bool has_nmap = false;  // some node carries a depth-shift texture: general trace kernel (kernels.cu: trace_general_kernel)
   int child_factor = 0;  // max secondary rays per ray (reflection + refraction possible in this scene)
   uint64_t n_bvh_nodes = 0, n_tris = 0, scene_bytes = 0;
   int grid_trace = 148, grid_tail = 148;
@@ -115,14 +116,21 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 bool shape_has_uv(int kind) { return kind == NRB_SHAPE_BALL || kind == NRB_SHAPE_CUBOID || kind == NRB_SHAPE_TRIMESH; }
 
-int relayout_bfs(std::vector<BvhNode> &nodes, int &root_all, int &root_opaque, std::vector<Candidate> &cands) {
+int relayout_bfs(std::vector<BvhNode> &nodes, int &root_all, int &root_opaque, std::vector<Candidate> &cands,
+                 std::vector<Candidate> &nmaps) {
   // Level-order relabel from root_all so the top of the tree is one contiguous prefix of the array
   // (what the closest-hit kernel touches for every ray; also the part worth staging on chip).
-  if (root_all < 0 || root_all == kEmpty || nodes.empty()) return 0;
+  if (nodes.empty()) return 0;
   std::vector<int> remap(nodes.size(), -1), order;
   order.reserve(nodes.size());
-  order.push_back(root_all);
-  remap[root_all] = 0;
+  auto add_root = [&](int r) {
+    if (r >= 0 && r != kEmpty && remap[r] < 0) {
+      remap[r] = (int)order.size();
+      order.push_back(r);
+    }
+  };
+  add_root(root_all);
+  for (auto &c : nmaps) add_root(c.root);  // depth-shift nodes keep their own sub-trees outside root_all
   for (size_t head = 0; head < order.size(); ++head) {
     const BvhNode &n = nodes[order[head]];
     int ch[2] = {n.n3.x, n.n3.y};
@@ -145,6 +153,7 @@ int relayout_bfs(std::vector<BvhNode> &nodes, int &root_all, int &root_opaque, s
   fix(root_all);
   fix(root_opaque);
   for (auto &c : cands) fix(c.root);
+  for (auto &c : nmaps) fix(c.root);
   nodes.swap(out);
   return 0;
 }
@@ -161,6 +170,7 @@ struct HostScene {
   std::vector<Light> lights;
   std::vector<int> planes;
   std::vector<Candidate> candidates;
+  std::vector<Candidate> nmaps;  // nodes with a depth-shift texture (SceneNode.nmap)
   int root_all = kEmpty, root_opaque = kEmpty;
   int shadow_samples = 0;
   bool any_refl = false, any_refr = false;
@@ -223,7 +233,7 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
   std::vector<Shape> shapes;
   std::vector<int> planes;
   std::vector<int> shape_of_node(d.n_nodes, -1);
-  std::vector<char> is_cand(d.n_nodes, 0);
+  std::vector<char> is_cand(d.n_nodes, 0), is_nmap(d.n_nodes, 0);
   bool any_refl = false, any_refr = false;
   uint64_t total_tris = 0;
   for (uint32_t i = 0; i < d.n_nodes; ++i) {
@@ -232,10 +242,10 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
       return fail(NRB_ERR_INVALID_ARG, "node " + std::to_string(i) + " material index out of range");
     if (n.shape < NRB_SHAPE_BALL || n.shape > NRB_SHAPE_TRIMESH)
       return fail(NRB_ERR_INVALID_ARG, "node " + std::to_string(i) + " has an unknown shape kind");
-    if (n.nmap_texture >= 0)
-      return fail(NRB_ERR_UNSUPPORTED, "node " + std::to_string(i) +
-                                           ": nmap depth shift (src/scene_node.rs:60-70) is not supported on device "
-                                           "(the reference loader never enables it: loader3d.rs:553)");
+    if (n.nmap_texture >= (int)d.n_textures)
+      return fail(NRB_ERR_INVALID_ARG, "node " + std::to_string(i) + " nmap texture index out of range");
+    // the depth shift applies only where the cast returns uvs (src/scene_node.rs:63); elsewhere the texture is inert
+    is_nmap[i] = (n.nmap_texture >= 0 && shape_has_uv(n.shape)) ? 1 : 0;
     const Material &m = materials[n.material];
     bool cand = (n.alpha < 1.0f) || (m.kind == NRB_MAT_PHONG && m.alpha_tex >= 0) ||
                 (m.kind == NRB_MAT_UV && !shape_has_uv(n.shape));
@@ -251,6 +261,7 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
     ni.alpha = n.alpha;
     ni.refr_coeff = (float)n.refr_coeff;
     ni.flags = cand ? 1 : 0;
+    ni.nmap_tex = is_nmap[i] ? n.nmap_texture : -1;
     node_info[i] = ni;
     if (n.shape == NRB_SHAPE_TRIMESH) {
       if (n.first_index % 3 != 0 || n.tri_count == 0 || n.first_index + 3 * n.tri_count > d.n_indices || !d.indices ||
@@ -406,7 +417,7 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
     std::vector<BuildItem> items;
     for (uint32_t i = 0; i < d.n_nodes; ++i) {
       const NrbNodeDesc &n = d.nodes[i];
-      if (n.shape != NRB_SHAPE_TRIMESH || is_cand[i]) continue;
+      if (n.shape != NRB_SHAPE_TRIMESH || is_cand[i] || is_nmap[i]) continue;
       for (uint64_t t = 0; t < n.tri_count; ++t) items.push_back(BuildItem{tri_box[node_tri_begin[i] + t], (int)(node_tri_begin[i] + t)});
     }
     if (!items.empty()) {
@@ -418,10 +429,45 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
     }
   }
   int depth_tri = bb.max_depth_seen;
-  std::vector<Candidate> candidates;
+  std::vector<Candidate> candidates, nmaps;
   for (uint32_t i = 0; i < d.n_nodes; ++i) {
     const NrbNodeDesc &n = d.nodes[i];
     if (n.shape == NRB_SHAPE_PLANE) continue;
+    if (is_nmap[i]) {
+      // own sub-root, outside every flat tree; the box is the REFERENCE's node AABB (HasBoundingVolume::bounding_volume:
+      // local box, centre transformed, half extents times |R|; ball: centre -+ r) because it decides the search order
+      Candidate c{};
+      c.node = (int)i;
+      double lc[3] = {0, 0, 0}, lhe[3] = {0, 0, 0};
+      if (n.shape == NRB_SHAPE_TRIMESH) {
+        std::vector<BuildItem> items;
+        for (uint64_t t = 0; t < n.tri_count; ++t) items.push_back(BuildItem{tri_box[node_tri_begin[i] + t], (int)(node_tri_begin[i] + t)});
+        Box rb;
+        bb.max_depth_seen = 0;
+        int code = kEmpty;
+        int brc = build_set(items, &rb, &code);
+        if (brc) return brc;
+        depth_tri = std::max(depth_tri, bb.max_depth_seen);
+        c.root = code;
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (uint64_t k = 0; k < 3 * n.tri_count; ++k) {
+          const float *p = d.positions + 3 * (n.vertex_base + d.indices[n.first_index + k]);
+          for (int a = 0; a < 3; ++a) lo[a] = std::min(lo[a], (double)p[a]), hi[a] = std::max(hi[a], (double)p[a]);
+        }
+        for (int a = 0; a < 3; ++a) lc[a] = 0.5 * (lo[a] + hi[a]), lhe[a] = 0.5 * (hi[a] - lo[a]);
+      } else {
+        c.root = make_leaf((uint32_t)shape_of_node[i], 1, true);
+        if (n.shape == NRB_SHAPE_CUBOID) lhe[0] = n.param[0], lhe[1] = n.param[1], lhe[2] = n.param[2];
+      }
+      for (int r = 0; r < 3; ++r) {
+        double cw = n.rot[3 * r] * lc[0] + n.rot[3 * r + 1] * lc[1] + n.rot[3 * r + 2] * lc[2] + n.trans[r];
+        double he = std::fabs(n.rot[3 * r]) * lhe[0] + std::fabs(n.rot[3 * r + 1]) * lhe[1] + std::fabs(n.rot[3 * r + 2]) * lhe[2];
+        if (n.shape == NRB_SHAPE_BALL) cw = n.trans[r], he = n.param[0];
+        c.lo[r] = (float)(cw - he), c.hi[r] = (float)(cw + he);
+      }
+      nmaps.push_back(c);
+      continue;
+    }
     if (n.shape == NRB_SHAPE_TRIMESH) {
       if (!is_cand[i]) continue;
       std::vector<BuildItem> items;
@@ -469,7 +515,8 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
   // one stack slot per level at most (the far child of each two-hit node) + the sentinel
   if (depth_tri + depth_mid + depth_top + 4 > kStackSize)
     return fail(NRB_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
-  relayout_bfs(bb.nodes, root_all, root_opaque, candidates);
+  if (nmaps.size() > 32) return fail(NRB_ERR_UNSUPPORTED, "more than 32 nodes with a depth-shift (nmap) texture");
+  relayout_bfs(bb.nodes, root_all, root_opaque, candidates, nmaps);
 
   // leaf-ordered triangle arrays
   H.tris.resize(bb.tri_order.size());
@@ -483,6 +530,7 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
   H.lights.swap(lights);
   H.planes.swap(planes);
   H.candidates.swap(candidates);
+  H.nmaps.swap(nmaps);
   H.root_all = root_all, H.root_opaque = root_opaque;
   H.shadow_samples = shadow_samples;
   H.any_refl = any_refl, H.any_refr = any_refr;
@@ -501,6 +549,7 @@ int check_bvh(const HostScene &H, std::string &why) {
   };
   std::vector<Item> stack;
   if (H.root_all != kEmpty) stack.push_back(Item{H.root_all, Box{}, false});
+  for (const Candidate &nm : H.nmaps) stack.push_back(Item{nm.root, Box{}, false});
   auto inside = [](const Box &outer, const Box &inner) {
     for (int k = 0; k < 3; ++k)
       if (inner.lo[k] < outer.lo[k] || inner.hi[k] > outer.hi[k]) return false;
@@ -600,6 +649,7 @@ int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
   CU(upload(S.d_lights, H.lights));
   CU(upload(S.d_planes, H.planes));
   CU(upload(S.d_candidates, H.candidates));
+  CU(upload(S.d_nmaps, H.nmaps));
   {
     size_t tb = std::max<size_t>(d.n_texels * 16, 16);
     CU(S.d_texels.ensure(tb));
@@ -617,6 +667,8 @@ int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
   v.lights = S.d_lights.as<Light>();
   v.planes = S.d_planes.as<int>();
   v.candidates = S.d_candidates.as<Candidate>();
+  v.nmaps = S.d_nmaps.as<Candidate>();
+  v.n_nmap = (int)H.nmaps.size();
   v.root_all = H.root_all;
   v.root_opaque = H.root_opaque;
   v.n_planes = (int)H.planes.size();
@@ -624,7 +676,8 @@ int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
   v.n_lights = (int)H.lights.size();
   v.shadow_samples = H.shadow_samples;
   for (int k = 0; k < 3; ++k) v.background[k] = d.background[k];
-  S.has_shapes = !H.shapes.empty();
+  S.has_nmap = !H.nmaps.empty();
+  S.has_shapes = !H.shapes.empty() || S.has_nmap;  // the general (HAS_SHAPES) kernel variants carry the nmap code
   S.child_factor = (H.any_refl ? 1 : 0) + (H.any_refr ? 1 : 0);
   S.n_bvh_nodes = H.nodes.size();
   S.n_tris = H.tris.size();
@@ -801,7 +854,10 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
       ShadowQueue sq{S.d_sq[0].as<float4>(), S.d_sq[1].as<float4>(), S.d_sq[2].as<float4>(), S.sq_cap};
       cudaEvent_t e0 = get_event(S, ev_used), e1 = get_event(S, ev_used);
       CU(cudaEventRecord(e0, st));
-      launch_trace(S.view, S.has_shapes, fp, primary, q, S.d_hits.as<float4>(), wcc, slot_lo, n_slots, sq, accum, wcs,
+      if (S.has_nmap)
+        launch_trace_general(S.view, fp, primary, q, S.d_hits.as<float4>(), wcc, slot_lo, n_slots, sq, accum, wcs, S.sm_count * 3, st);
+      else
+        launch_trace(S.view, S.has_shapes, fp, primary, q, S.d_hits.as<float4>(), wcc, slot_lo, n_slots, sq, accum, wcs,
                    TraceOpts{primary ? refill_primary : refill_rays, refill_shadow, reverse_shadow, small_queue}, S.grid_trace, st);
       CU(cudaEventRecord(e1, st));
       trace_spans.emplace_back(e0, e1);

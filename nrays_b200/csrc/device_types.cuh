@@ -66,7 +66,8 @@ struct __align__(16) NodeInfo {
   float alpha;
   float refr_coeff;
   int flags;  // bit0: shadow-transparent candidate (own BVH root)
-  int _pad[2];
+  int nmap_tex;  // SceneNode.nmap (src/scene_node.rs:60-70): texture whose mean rgb is subtracted from the node's toi, or -1
+  int _pad;
 };
 
 struct __align__(16) Material {  // 64 bytes
@@ -115,10 +116,12 @@ struct SceneView {
   const Light *lights;
   const int *planes;            // shape indices of all planes (always tested, never in the BVH)
   const Candidate *candidates;  // shadow-transparent candidates that are not planes
+  const Candidate *nmaps;       // nodes with a depth-shift texture: own sub-root, box = the REFERENCE's node AABB (pruning order)
   int root_all;                 // closest-hit entry (kEmpty if the scene has only planes)
   int root_opaque;              // any-hit entry for shadow rays (kEmpty if none)
   int n_planes;
   int n_candidates;
+  int n_nmap;
   int n_lights;
   int shadow_samples;  // sum over lights of racsample^2
   float background[3];

@@ -390,6 +390,9 @@ NRB_DI uint32_t pool_assign(RayPool *pool, bool idle, uint32_t *cursor, uint32_t
   return mine;
 }
 
+// SceneNode.nmap (src/scene_node.rs:60-70): defined after the surface reconstruction below.
+NRB_DI void nmap_closest(const SceneView &sc, V3 o, V3 d, Hit &hit);
+
 // ---------------------------------------------------------------------------------------------
 // K2 — closest hit of one ray (Scene::trace's best_first_search, src/scene.rs:164-166)
 // ---------------------------------------------------------------------------------------------
@@ -408,6 +411,7 @@ NRB_DI float4 closest_hit(const SceneView &sc, V3 o, V3 d) {
     }
   }
   if (sc.root_all != kEmpty) traverse<HAS_SHAPES, false>(sc, sc.root_all, o, d, hit.t, hit);
+  if (HAS_SHAPES && sc.n_nmap > 0) nmap_closest(sc, o, d, hit);
   return make_float4(hit.t, __uint_as_float(hit.prim), hit.u, hit.v);
 }
 
@@ -464,6 +468,92 @@ NRB_DI float4 mat_ambiant(const SceneView &sc, const Material &m, const Surface 
     return make_float4(m.ambient[0] * tc.x, m.ambient[1] * tc.y, m.ambient[2] * tc.z, tc.w);
   }
   return make_float4(m.ambient[0], m.ambient[1], m.ambient[2], 1.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SceneNode.nmap — the "normal map" of the reference is a depth shift (src/scene_node.rs:60-70): after the node's own
+// cast, `toi -= mean(nmap.sample(uv).rgb)`.  The shifted toi is what best_first_search compares, so a node with a
+// depth-shift texture cannot live in the flat trees: it keeps its own sub-root and is resolved after the rest of the
+// scene, in the order and with the pruning of the reference's search — nodes are popped by increasing AABB entry
+// distance and the search stops at the first one whose entry distance is >= the best cost so far;
+// `Candidate.lo/hi` hold the REFERENCE's node AABB (centre transformed, half extents times |R|) for that purpose.
+// The loader never enables nmap (examples/loader3d.rs:553); this is the general, non-resumable path.
+// ---------------------------------------------------------------------------------------------
+NRB_DI bool aabb_toi_solid(const float lo[3], const float hi[3], V3 o, V3 d, float &toi) {  // AABB::toi_with_ray(.., solid = true), SURVEY B.3
+  float tmin = 0.0f, tmax = 3.402823466e+38f;
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    const float oi = comp(o, ax), di = comp(d, ax);
+    if (di == 0.0f) {
+      if (oi < lo[ax] || oi > hi[ax]) return false;
+    } else {
+      const float inv = 1.0f / di;
+      float t0 = (lo[ax] - oi) * inv, t1 = (hi[ax] - oi) * inv;
+      if (t0 > t1) {
+        const float tmp = t0;
+        t0 = t1, t1 = tmp;
+      }
+      tmin = fmaxf(tmin, t0);
+      tmax = fminf(tmax, t1);
+      if (tmin > tmax) return false;
+    }
+  }
+  toi = tmin;
+  return true;
+}
+
+// Closest hit of one nmap node with its toi shifted; false if the node is missed.
+NRB_DI bool nmap_cast(const SceneView &sc, const Candidate &nm, V3 o, V3 d, Hit &h) {
+  h.t = 3.402823466e+38f, h.prim = kMiss, h.u = h.v = 0.0f;
+  if (!traverse<true, false>(sc, nm.root, o, d, 3.402823466e+38f, h)) return false;
+  Surface sf;
+  reconstruct<true>(sc, o, d, h.prim, h.u, h.v, sf);
+  if (sf.has_uv) {
+    const float4 c = tex_sample(sc, sc.node_info[nm.node].nmap_tex, sf.u, sf.v);
+    h.t -= (c.x + c.y + c.z) / 3.0f;
+  }
+  return true;
+}
+
+NRB_DI void nmap_closest(const SceneView &sc, V3 o, V3 d, Hit &hit) {
+  uint32_t done = 0u;
+  for (int it = 0; it < sc.n_nmap; ++it) {
+    int next = -1;
+    float next_tb = 3.402823466e+38f;
+    for (int j = 0; j < sc.n_nmap; ++j) {
+      if ((done >> j) & 1u) continue;
+      float tb;
+      if (!aabb_toi_solid(sc.nmaps[j].lo, sc.nmaps[j].hi, o, d, tb)) {
+        done |= 1u << j;
+        continue;
+      }
+      if (tb < next_tb) next_tb = tb, next = j;
+    }
+    if (next < 0 || !(next_tb < hit.t)) break;  // popped cost >= best cost: the search ends
+    done |= 1u << next;
+    Hit h;
+    if (nmap_cast(sc, sc.nmaps[next], o, d, h) && h.t < hit.t) hit = h;
+  }
+}
+
+// Shadow query over the nmap nodes (src/scene.rs:304-339 with the shifted toi).  Returns true if occluded.
+NRB_DI bool nmap_shadow(const SceneView &sc, V3 o, V3 d, float tmax, V3 &filter) {
+  for (int j = 0; j < sc.n_nmap; ++j) {
+    const Candidate nm = sc.nmaps[j];
+    float tb;
+    if (!aabb_toi_solid(nm.lo, nm.hi, o, d, tb)) continue;
+    Hit h;
+    if (!nmap_cast(sc, nm, o, d, h) || !(h.t <= tmax)) continue;
+    Surface sf;
+    reconstruct<true>(sc, o, d, h.prim, h.u, h.v, sf);
+    const NodeInfo ni = sc.node_info[nm.node];
+    const float4 c = mat_ambiant(sc, sc.materials[ni.material], sf);
+    const float alpha = c.w * ni.alpha;
+    if (!(alpha < 1.0f)) return true;
+    const float k = 1.0f - alpha;
+    filter = mk(filter.x * c.x * k, filter.y * c.y * k, filter.z * c.z * k);
+  }
+  return false;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -543,6 +633,7 @@ NRB_DI void shadow_query(const SceneView &sc, V3 o, V3 d, float tmax, uint32_t p
     occluded = traverse<HAS_SHAPES, true>(sc, sc.root_opaque, o, d, tmax, h);
   }
   if (!occluded) occluded = shadow_candidates<HAS_SHAPES>(sc, o, d, tmax, filter);
+  if (HAS_SHAPES && !occluded && sc.n_nmap > 0) occluded = nmap_shadow(sc, o, d, tmax, filter);
   if (!occluded) accum_add(accum, pix, cmul(contrib, filter));
 }
 
@@ -740,6 +831,51 @@ __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 6 : kTraceMinBlocks)
     } else {
       if (wc_shadow)
         drain_shadow<HAS_SHAPES>(sc, sq, accum, wc_shadow, opts.min_active_shadow, opts.reverse_shadow != 0, opts.small_queue, pool, lm);
+    }
+  }
+}
+
+// General form of the trace kernel for scenes the resumable loop does not cover (nodes with a depth-shift texture):
+// same queues and counters, one 32-ray packet per fetch, every lane runs the whole query (closest_hit / shadow_query).
+template <bool PRIMARY>
+__global__ void __launch_bounds__(kTraceBlock, 3)
+    trace_general_kernel(SceneView sc, FrameParams fp, RayQueue q, float4 *hits, WaveCounters *wc_closest, uint32_t slot_lo,
+                         uint32_t n_slots, ShadowQueue sq, float4 *accum, WaveCounters *wc_shadow) {
+  const uint32_t lane = lane_id();
+  if (wc_shadow) {
+    const uint32_t count = min(wc_shadow->n_shadow, sq.capacity);
+    while (true) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&wc_shadow->fetch_shadow, 32u);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (base >= count) break;
+      const uint32_t i = base + lane;
+      if (i < count) {
+        const float4 a = sq.a[i], b = sq.b[i], c = sq.c[i];
+        shadow_query<true>(sc, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), a.w, __float_as_uint(b.w), mk(c.x, c.y, c.z), accum);
+      }
+    }
+  }
+  if (wc_closest) {
+    const uint32_t count = PRIMARY ? n_slots : wc_closest->n_rays;
+    while (true) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&wc_closest->fetch_closest, 32u);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (base >= count) break;
+      const uint32_t i = base + lane;
+      if (i < count) {
+        V3 o, d;
+        bool valid = true;
+        if (PRIMARY) {
+          uint32_t gid;
+          valid = primary_ray(fp, slot_lo + i, o, d, gid);
+        } else {
+          const float4 a = q.a[i], b = q.b[i];
+          o = mk(a.x, a.y, a.z), d = mk(a.w, b.x, b.y);
+        }
+        hits[i] = valid ? closest_hit<true>(sc, o, d) : make_float4(0.0f, __uint_as_float(kSkip), 0.0f, 0.0f);
+      }
     }
   }
 }
@@ -1190,6 +1326,16 @@ void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, b
     if (primary) NRB_LAUNCH_TRACE(false, true); else NRB_LAUNCH_TRACE(false, false);
   }
 #undef NRB_LAUNCH_TRACE
+}
+
+void launch_trace_general(const SceneView &sc, const FrameParams &fp, bool primary, RayQueue q, float4 *hits,
+                          WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, ShadowQueue sq, float4 *accum,
+                          WaveCounters *wc_shadow, int grid, cudaStream_t st) {
+  if (!wc_closest && !wc_shadow) return;
+  if (primary)
+    trace_general_kernel<true><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow);
+  else
+    trace_general_kernel<false><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow);
 }
 
 void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue qin,

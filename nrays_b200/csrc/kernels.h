@@ -40,6 +40,10 @@ struct TraceOpts {
 void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue q, float4 *hits,
                   WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, ShadowQueue sq, float4 *accum,
                   WaveCounters *wc_shadow, TraceOpts opts, int grid, cudaStream_t st);
+// scenes with depth-shift (nmap) nodes: general packet kernel, every lane runs the whole query
+void launch_trace_general(const SceneView &sc, const FrameParams &fp, bool primary, RayQueue q, float4 *hits,
+                          WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, ShadowQueue sq, float4 *accum,
+                          WaveCounters *wc_shadow, int grid, cudaStream_t st);
 void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, bool primary, RayQueue qin,
                   const float4 *hits, WaveCounters *wc, uint32_t slot_lo, uint32_t n_slots, uint32_t lo, uint32_t hi,
                   RayQueue qout, ShadowQueue sq, Counters *ctr, float4 *accum, int grid, cudaStream_t st);

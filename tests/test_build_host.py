@@ -64,8 +64,8 @@ def test_malformed_tables_are_rejected_without_a_device():
     assert validate(f)[0] == A.NRB_ERR_INVALID_ARG
     f = flat(); f.indices[2] = 77
     assert validate(f)[0] == A.NRB_ERR_INVALID_ARG
-    f = flat(); f.node_rows[0].nmap_texture = 0
-    assert validate(f)[0] == A.NRB_ERR_UNSUPPORTED
+    f = flat(); f.node_rows[0].nmap_texture = 5     # no such texture
+    assert validate(f)[0] == A.NRB_ERR_INVALID_ARG
     f = flat(); f.desc.struct_size = 8
     assert validate(f)[0] == A.NRB_ERR_INVALID_ARG
     f = flat(); f.mat_rows[0].kind = 9

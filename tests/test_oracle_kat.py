@@ -253,3 +253,54 @@ def test_f32_twin_agrees_with_f64_on_primitives():
 def test_light_racsample_is_floor_sqrt():
     # ((nsample as f32).sqrt()) as usize — src/light.rs:20 (nsample 10 -> 3, 50 -> 7)
     assert [Light((0, 0, 0), 0, n, (1, 1, 1)).racsample for n in (1, 3, 4, 10, 50, 100)] == [1, 1, 2, 3, 7, 10]
+
+
+# ---- SceneNode.nmap: the depth shift of src/scene_node.rs:60-70 -------------------------------------
+def _const_tex(rgb):
+    from nrays_b200 import ImageData, Interpolation, Overflow, Texture2d
+
+    px = np.ones((4, 4), np.float32)
+    px[:, :3] = rgb
+    return Texture2d(ImageData(px, (2, 2)), Interpolation.Bilinear, Overflow.Wrap)
+
+
+def test_nmap_shifts_toi_by_the_mean_texel_and_only_where_the_cast_has_uvs():
+    from nrays_b200 import make_camera
+
+    def scene(nodes):
+        return O.OracleScene(Scene(nodes, [], upload=False).flat, 64)
+
+    def n(geom, nmap, pos=(0, 0, 0), mat=None):
+        return SceneNode(mat or NormalMaterial(), 0, 0, 1.0, 1.0, Isometry3.new(pos, (0, 0, 0)), geom, nmap, False)
+
+    # unit ball: toi 4 -> 4 - (0.3 + 0.6 + 0.9) / 3 = 3.4; normal and uv are those of the real hit
+    r = scene([n(Ball(1.0), _const_tex((0.3, 0.6, 0.9)))]).cast(0, (0, 0, -5), (0, 0, 1))
+    assert r["toi"] == pytest.approx(4.0 - 0.6, abs=1e-6)
+    np.testing.assert_allclose(r["normal"], (0, 0, -1), atol=1e-12)
+    np.testing.assert_allclose(r["uv"], (0.25, 0.5), atol=1e-12)
+    # cylinder casts return no uvs: the texture is inert
+    r = scene([n(Cylinder(1.0, 1.0), _const_tex((0.9, 0.9, 0.9)))]).cast(0, (0, 0, -5), (0, 0, 1))
+    assert r["toi"] == pytest.approx(4.0)
+    # best-first order: the far ball's shifted toi (7 - 3.5 = 3.5... here 6 - 0.9 = 5.1) would beat nothing; a far
+    # node whose AABB starts behind the current best is never cast, even though its shifted toi would win
+    cam = make_camera(4, 4, 1, 0.0, (0, 0, -5), np.eye(4), seed=0)
+    from nrays_b200 import UVMaterial
+    near = n(Ball(1.0), None)
+    far_small = n(Ball(1.0), _const_tex((0.5, 0.5, 0.5)), (0, 0, 2.2), UVMaterial())
+    far_big = n(Ball(1.0), _const_tex((3.0, 3.0, 3.0)), (0, 0, 2.2), UVMaterial())   # shifted toi 6.2 - 3 = 3.2 < 4
+    # near ball: toi 4, normal (0,0,-1) -> NormalMaterial colour (.5,.5,0).  far ball (uv colour (.25,.5,0)): AABB entry
+    # 6.2 >= 4 -> pruned by the search, whatever its shift
+    for far in (far_small, far_big):
+        rgb = scene([near, far]).trace(cam, (0, 0, -5), (0, 0, 1))
+        np.testing.assert_allclose(rgb, (0.5, 0.5, 0.0), atol=1e-6)
+    # ... but a far node whose AABB starts before the best cost IS cast and wins with its shifted toi
+    rgb = scene([near, n(Ball(1.0), _const_tex((0.5, 0.5, 0.5)), (0, 0, -0.2), UVMaterial())]).trace(cam, (0, 0, -5), (0, 0, 1))
+    np.testing.assert_allclose(rgb, (0.25, 0.5, 0.0), atol=1e-6)
+    # overlapping boxes: far ball at z = 0.5 has AABB entry 4.5 >= 4 -> still pruned; at z = -0.2 (entry 3.8 < 4) it is cast,
+    # its real toi is 3.8, shifted 3.8 - 0.5 = 3.3 < 4 -> it wins; its normal is (0,0,-1) too, so compare through toi
+    s = scene([near, n(Ball(1.0), _const_tex((0.5, 0.5, 0.5)), (0, 0, -0.2))])
+    assert s.cast(1, (0, 0, -5), (0, 0, 1))["toi"] == pytest.approx(3.3, abs=1e-6)
+    # shadow query: the shifted toi is what is compared with maxtoi (src/scene.rs:313)
+    s = scene([n(Ball(1.0), _const_tex((0.6, 0.6, 0.6)))])
+    assert s.intersects_ray((0, 0, -5), (0, 0, 1), 3.5) is None          # 4 - 0.6 = 3.4 <= 3.5: occluded
+    assert s.intersects_ray((0, 0, -5), (0, 0, 1), 3.3) is not None      # 3.4 > 3.3: free

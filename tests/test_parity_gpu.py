@@ -94,6 +94,46 @@ def test_alpha_mapped_mesh_and_per_node_shadow_semantics(gpu):
     assert st.rays_total == st.rays_reference - st.rays_shadow_culled
 
 
+def _shift_texture(lo, hi, seed, size=(8, 8)):
+    rng = np.random.default_rng(seed)
+    px = np.ones((size[0] * size[1], 4), np.float32)
+    px[:, :3] = rng.uniform(lo, hi, (size[0] * size[1], 3)).astype(np.float32)
+    return Texture2d(ImageData(px, size), Interpolation.Bilinear, Overflow.Wrap)
+
+
+def test_nmap_depth_shift_nodes(gpu):
+    """SceneNode.nmap (src/scene_node.rs:60-70): toi -= mean(nmap.sample(uv).rgb) after the node's own cast, on a ball, a
+    rotated cuboid and a mesh, next to plain nodes, with shadows, a reflective plane and a transparent shifted node —
+    the shifted toi decides closest hits, hit points and shadow occlusion, in the reference's best-first order."""
+    from nrays_b200 import Isometry3, SceneNode
+
+    def shifted(geom, mat, nmap, pos, angle=(0, 0, 0), alpha=1.0):
+        return SceneNode(mat, 0.0, 0.0, alpha, 1.0, Isometry3.new(pos, np.radians(angle)), geom, nmap, False)
+
+    P, F, UV = quad_mesh(1.2, 5, y=0.0)
+    nodes = [shifted(Ball(0.9), phong(ka=(0.2, 0.1, 0.1)), _shift_texture(0.0, 0.6, 1), (-2.2, 0.2, 0.0)),
+             shifted(Cuboid((0.7, 0.6, 0.5)), phong(ka=(0.1, 0.2, 0.1)), _shift_texture(0.1, 0.4, 2), (0.0, 0.1, 0.4), (20, 35, 10)),
+             shifted(TriMesh(P, F, UV), phong(ka=(0.1, 0.1, 0.3)), _shift_texture(0.0, 0.8, 3, (5, 7)), (2.3, 0.3, 0.2), (-50, 0, 15)),
+             shifted(Ball(0.5), phong(ka=(0.3, 0.3, 0.1)), _shift_texture(0.2, 0.3, 4), (0.9, 1.4, -0.8), alpha=0.5),
+             shifted(Cylinder(0.6, 0.4), phong(), _shift_texture(0.5, 0.9, 5), (-0.9, 1.3, 0.9)),   # no uvs: the texture is inert
+             node(Ball(0.6), phong(), pos=(-0.2, -0.2, -1.6)), node(Cuboid((0.4, 0.4, 0.4)), NormalMaterial(), pos=(1.6, -0.4, -1.2)),
+             node(Plane((0, 1, 0)), phong(), pos=(0, -1.2, 0), refl=(0.3, 0.5))]
+    lights = [Light((1.5, 5.0, -3.0), 0.0, 1, (1, 1, 1)), Light((-3.0, 4.0, -2.0), 0.3, 4, (0.6, 0.6, 0.9))]
+    img, st, ref, ost = render_both(nodes, lights, eye=(0.3, 1.6, -6.5), w=160, h=112, spp=2, window=1.0, seed=3)
+    assert_parity(img, ref, max_frac=3e-3, what="nmap")
+    assert_counts_close(st, ost)
+    # and the shift is really in the picture: the same scene without the textures differs
+    plain = [SceneNode(n.material, n.refl_mix, n.refl_atenuation, n.alpha, n.refr_coeff, n.transform, n.geometry, None, n.solid) for n in nodes]
+    img0, _, _, _ = render_both(plain, lights, eye=(0.3, 1.6, -6.5), w=160, h=112, spp=2, window=1.0, seed=3)
+    assert (np.abs(img0 - img).max(axis=1) > 0.02).mean() > 0.02
+    # all driver paths agree on it (tail / no tail / tiny batches)
+    for env in (dict(NRB_TAIL_RAYS=0), dict(NRB_TAIL_RAYS=1 << 30), dict(NRB_BATCH_SLOTS=4096, NRB_SHADOW_CAP=2048)):
+        with _Env(**env):
+            img2, st2, _, _ = render_both(nodes, lights, eye=(0.3, 1.6, -6.5), w=160, h=112, spp=2, window=1.0, seed=3)
+        np.testing.assert_allclose(img2, img, rtol=0, atol=3e-5, err_msg=str(env))
+        assert st2.rays_reference == st.rays_reference
+
+
 def test_solid_flag_and_camera_inside_objects(gpu):
     nodes = [node(Ball(3.0), phong(), pos=(0, 0, 0), solid=False), node(Cuboid((0.5, 0.5, 0.5)), NormalMaterial(), pos=(0, 0, 1.5)),
              node(Cylinder(0.4, 0.3), UVMaterial(), pos=(1.2, 0, 1.0))]
@@ -166,8 +206,8 @@ def test_error_codes(gpu):
     h = C.c_void_p()
     assert lib.nrb_scene_create(C.byref(flat.desc), 0, C.byref(h)) == A.NRB_ERR_INVALID_ARG
     flat = Scene([node(Ball(1.0), NormalMaterial())], [], upload=False).flat
-    flat.node_rows[0].nmap_texture = 0
-    assert lib.nrb_scene_create(C.byref(flat.desc), 0, C.byref(h)) == A.NRB_ERR_UNSUPPORTED
+    flat.node_rows[0].nmap_texture = 3      # no such texture
+    assert lib.nrb_scene_create(C.byref(flat.desc), 0, C.byref(h)) == A.NRB_ERR_INVALID_ARG
     Pm, Fm, UVm = quad_mesh(1.0, 1)
     flat = Scene([node(TriMesh(Pm, Fm, UVm), NormalMaterial())], [], upload=False).flat
     flat.indices[0] = 1000
