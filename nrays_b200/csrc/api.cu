@@ -97,6 +97,10 @@ struct NrbScene {
   int grid_shade = 148;
   std::vector<cudaEvent_t> events;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  // nrb_render: the image's device->host copy runs on its own stream while the tail phase finishes, then the pixels the
+  // tail changed follow as an ordered patch
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_early = nullptr, ev_copied = nullptr;
 
   ~NrbScene() {
     cudaSetDevice(device);
@@ -106,6 +110,9 @@ struct NrbScene {
     if (ev_begin) cudaEventDestroy(ev_begin);
     if (ev_end) cudaEventDestroy(ev_end);
     if (own_stream) cudaStreamDestroy(own_stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (ev_early) cudaEventDestroy(ev_early);
+    if (ev_copied) cudaEventDestroy(ev_copied);
   }
 };
 
@@ -765,8 +772,13 @@ cudaEvent_t get_event(NrbScene &S, size_t &used) {
 // Renders into S.d_accum and resolves to `d_out` (device; float rgb or u8 rgb).
 // `to_image`: with a tile set, resolve this rank's tiles into the row-major image `d_out` (possibly peer memory)
 // instead of the packed tile buffer.
+// `early_h_out` (nrb_render with a pinned, device-mapped destination; `early_d_out` is the same memory as the device
+// sees it): when the frame reaches its tail phase, the image as it stands is resolved and its device->host copy starts on
+// S.copy_stream, overlapping the tail; the final resolve is replaced by a kernel that stores the pixels the tail
+// changed straight into the host image once that copy has landed.  *early_used tells the caller which happened.
 int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, float *d_out, uint8_t *d_out8,
-                  uint32_t *n_local_tiles, NrbStats *stats, bool to_image = false) {
+                  uint32_t *n_local_tiles, NrbStats *stats, bool to_image = false, float *early_h_out = nullptr,
+                  float *early_d_out = nullptr, bool *early_used = nullptr) {
   CU(cudaSetDevice(S.device));
   FrameParams fp;
   int rc = make_frame_params(cam, tiles, fp);
@@ -877,6 +889,16 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
         if (known_prev == 0 || S.child_factor == 0) break;
         bound = known_prev * (uint64_t)S.child_factor;
         if (k >= tail_min_wave && bound <= tail_threshold) {
+          if (early_h_out && early_used && !*early_used && fp.n_local_tiles <= tiles_per_batch && d_out && !fp.packed) {
+            // everything but the tail phase is in the accumulator: send the image now, patch it afterwards
+            launch_resolve(accum, n_acc, fp.spp, d_out, st);
+            ++launches;
+            CU(cudaEventRecord(S.ev_early, st));
+            CU(cudaStreamWaitEvent(S.copy_stream, S.ev_early, 0));
+            CU(cudaMemcpyAsync(early_h_out, d_out, (size_t)n_acc * 3 * sizeof(float), cudaMemcpyDeviceToHost, S.copy_stream));
+            CU(cudaEventRecord(S.ev_copied, S.copy_stream));
+            *early_used = true;
+          }
           // ---- tail: every lane follows its own ray chain to the end (see tail_kernel) -----------
           // The chains append their shadow rays behind the ones the last shade left untraced (same queue,
           // same counter); ONE shadow launch per tail launch traces them all.
@@ -1010,7 +1032,10 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
       if (rc) return rc;
     }
   }
-  if (d_out8)
+  if (early_used && *early_used) {
+    CU(cudaStreamWaitEvent(st, S.ev_copied, 0));  // the early image must have landed before its pixels are overwritten
+    launch_patch_host_image(accum, d_out, n_acc, fp.spp, early_d_out, st);
+  } else if (d_out8)
     launch_resolve_rgb8(accum, n_acc, fp.spp, d_out8, st);
   else if (to_image && fp.packed)
     launch_resolve_tiles_to_image(accum, fp, d_out, st);
@@ -1209,10 +1234,35 @@ int nrb_render(NrbScene *scene, const NrbCamera *camera, float *out_rgb, NrbStat
   CU(cudaSetDevice(scene->device));
   size_t bytes = (size_t)camera->width * camera->height * 3 * sizeof(float);
   CU(scene->d_out.ensure(std::max<size_t>(bytes, 16)));
-  int rc = render_device(*scene, *camera, nullptr, scene->d_out.as<float>(), nullptr, nullptr, stats);
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(out_rgb, scene->d_out.p, bytes, cudaMemcpyDeviceToHost, scene->stream));
-  CU(cudaStreamSynchronize(scene->stream));
+  // With a pinned destination the copy can run beside the tail phase (render_device: early_h_out); a pageable one would
+  // make cudaMemcpyAsync block the host in the middle of the frame, so it keeps the plain render -> copy order.
+  float *mapped = nullptr;  // the destination as the device sees it, if it is pinned and mapped
+  if (env_size("NRB_EARLY_COPY", 1) != 0) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, out_rgb) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+      void *dp = nullptr;
+      if (cudaHostGetDevicePointer(&dp, out_rgb, 0) == cudaSuccess) mapped = (float *)dp;
+    }
+    cudaGetLastError();
+  }
+  if (mapped && !scene->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&scene->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&scene->ev_early, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&scene->ev_copied, cudaEventDisableTiming));
+  }
+  bool early = false;
+  int rc = render_device(*scene, *camera, nullptr, scene->d_out.as<float>(), nullptr, nullptr, stats, false,
+                         mapped ? out_rgb : nullptr, mapped, mapped ? &early : nullptr);
+  if (rc) {
+    if (early) cudaEventSynchronize(scene->ev_copied);
+    return rc;
+  }
+  if (!early) {
+    CU(cudaMemcpyAsync(out_rgb, scene->d_out.p, bytes, cudaMemcpyDeviceToHost, scene->stream));
+    CU(cudaStreamSynchronize(scene->stream));
+  }
+  // early: the copy ran beside the tail phase and the patch kernel has stored what the tail changed (render_device
+  // returns after synchronising the stream): the host image is complete
   return NRB_OK;
 }
 

@@ -1268,6 +1268,18 @@ __global__ void resolve_rgb8_kernel(const float4 *accum, uint32_t n, float spp, 
   }
 }
 
+// nrb_render with a pinned destination: the image's device->host copy is started when the frame enters its tail phase
+// and overlaps it; afterwards this kernel stores the pixels the tail changed straight into the (mapped) host image.
+// Neighbouring changed pixels leave a warp as contiguous segments, so the PCIe writes are mostly full packets.
+__global__ void patch_host_image_kernel(const float4 *accum, const float *early_rgb, uint32_t n, float spp, float *host_rgb) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = accum[i];
+  const float r = a.x / spp, g = a.y / spp, b = a.z / spp;
+  const size_t o = 3 * (size_t)i;
+  if (r != early_rgb[o] || g != early_rgb[o + 1] || b != early_rgb[o + 2]) host_rgb[o] = r, host_rgb[o + 1] = g, host_rgb[o + 2] = b;
+}
+
 // K5 + K6 fused for the multi-GPU path: this rank's packed tile accumulators are resolved (/ spp) straight into the
 // ROW-MAJOR image `out_rgb`, which may live on another GPU (peer / IPC-mapped memory over NVLink): the finished
 // pixels cross the link once, as 48-byte stores of four pixels, and nothing is gathered or un-tiled afterwards.
@@ -1385,6 +1397,11 @@ void launch_resolve(const float4 *accum, uint32_t n, uint32_t spp, float *out_rg
 void launch_resolve_rgb8(const float4 *accum, uint32_t n, uint32_t spp, uint8_t *out, cudaStream_t st) {
   if (!n) return;
   resolve_rgb8_kernel<<<(n + 255) / 256, 256, 0, st>>>(accum, n, (float)spp, out);
+}
+
+void launch_patch_host_image(const float4 *accum, const float *early_rgb, uint32_t n, uint32_t spp, float *host_rgb, cudaStream_t st) {
+  if (!n) return;
+  patch_host_image_kernel<<<(n + 255) / 256, 256, 0, st>>>(accum, early_rgb, n, (float)spp, host_rgb);
 }
 
 void launch_resolve_tiles_to_image(const float4 *accum, const FrameParams &fp, float *out_rgb, cudaStream_t st) {

@@ -10,10 +10,28 @@ import oracle_lib as O
 from nrays_b200 import (Ball, Capsule, Cone, Cuboid, Cylinder, ImageData, Interpolation, Isometry3, Light,
                         NormalMaterial, Overflow, PhongMaterial, Plane, Scene, SceneNode, Texture2d, TriMesh, UVMaterial,
                         _abi as A, _lib, camera_projection, configs, make_camera, render)
-from util import (TOL, assert_counts_close, assert_parity, checker_texture, default_phong, image_metrics, node, quad_mesh,
+from util import (TOL, assert_counts_close, assert_parity, checker_texture, default_phong, image_metrics, look, node, quad_mesh,
                   render_both)
 
 pytestmark = pytest.mark.gpu
+
+
+class _Env:
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        import os
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        import os
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 def phong(ka=(0.1, 0.1, 0.1), kd=(0.8, 0.7, 0.6), ks=(0.5, 0.5, 0.5), ns=40.0, tex=None, amap=None):
@@ -232,6 +250,46 @@ def test_rgb8_output_is_the_png_quantisation(gpu):
     scene.close()
 
 
+def test_pinned_destination_overlaps_the_copy_and_patches_the_tail(gpu):
+    """nrb_render into PINNED host memory starts the image's device->host copy when the frame enters its tail phase and
+    then stores the pixels the tail changed straight into the (mapped) host image; the result is the image of the plain path."""
+    scene, camd, cfg = configs.build("C3", target_tris=30000, lod=4)   # alpha-mapped foliage: a real tail phase
+    w, h = 208, 117
+    cam = make_camera(w, h, 3, 1.0, camd.eye, camd.projection((w, h)), seed=11)
+    n = w * h * 3
+
+    def go(ptr):
+        st = A.NrbStats()
+        _lib.check(gpu.nrb_render(scene.handle, C.byref(cam), C.cast(ptr, C.POINTER(C.c_float)), C.byref(st)))
+        return st
+
+    pageable = np.full(n, -1.0, np.float32)
+    st_a = go(pageable.ctypes.data)
+    hp = gpu.nrb_host_alloc(n * 4)
+    pinned = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_float)), shape=(n,))
+    pinned[:] = -2.0
+    st_b = go(hp)
+    np.testing.assert_allclose(pinned, pageable, rtol=0, atol=3e-5)
+    assert st_b.rays_total == st_a.rays_total
+    assert st_b.kernel_launches == st_a.kernel_launches + 1      # early resolve + patch kernel instead of one resolve
+    with _Env(NRB_EARLY_COPY=0):
+        pinned[:] = -3.0
+        st_c = go(hp)
+    np.testing.assert_allclose(pinned, pageable, rtol=0, atol=3e-5)
+    assert st_c.kernel_launches == st_a.kernel_launches
+    # a frame without a tail phase (one opaque ball, no lights) takes the plain path even with a pinned destination
+    scene.close()
+    plain = Scene([node(Ball(1.0), NormalMaterial())], [], (0.2, 0.3, 0.4))
+    cam2 = make_camera(64, 48, 1, 0.0, (0, 0, -5), look((0, 0, -5), (0, 0, 0), 45.0, 64, 48), seed=0)
+    st = A.NrbStats()
+    _lib.check(gpu.nrb_render(plain.handle, C.byref(cam2), C.cast(hp, C.POINTER(C.c_float)), C.byref(st)))
+    ref = np.empty(64 * 48 * 3, np.float32)
+    _lib.check(gpu.nrb_render(plain.handle, C.byref(cam2), ref.ctypes.data_as(C.POINTER(C.c_float)), None))
+    np.testing.assert_array_equal(pinned[:64 * 48 * 3], ref)
+    plain.close()
+    gpu.nrb_host_free(hp)
+
+
 def test_tile_sharded_render_equals_full_frame(gpu):
     """8 virtual ranks on one GPU: packed tiles + un-tile == the unsharded frame (RNG keyed by global pixel)."""
     import torch
@@ -289,24 +347,6 @@ def test_tiles_resolved_straight_into_the_image(gpu, w, h, world):
 
 
 # ---- driver paths that the default sizes never reach -------------------------------------------------
-class _Env:
-    def __init__(self, **kv):
-        self.kv = {k: str(v) for k, v in kv.items()}
-
-    def __enter__(self):
-        import os
-        self.old = {k: os.environ.get(k) for k in self.kv}
-        os.environ.update(self.kv)
-
-    def __exit__(self, *a):
-        import os
-        for k, v in self.old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
-
-
 def _glass_mirror_scene():
     """Nodes that spawn BOTH children (refl_mix > 0 and alpha < 1): the tail kernel must spill one."""
     nodes = [node(Ball(0.9), phong(ka=(0.2, 0.1, 0.1)), pos=(-1.2, 0, 0), alpha=0.4, refr=1.2, refl=(0.3, 0.3)),
