@@ -889,7 +889,10 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
         if (known_prev == 0 || S.child_factor == 0) break;
         bound = known_prev * (uint64_t)S.child_factor;
         if (k >= tail_min_wave && bound <= tail_threshold) {
-          if (early_h_out && early_used && !*early_used && fp.n_local_tiles <= tiles_per_batch && d_out && !fp.packed) {
+          // (every ray of the tail phase descends from a ray of wave k-1, so at most known_prev pixels can still change;
+          //  with more than that the patch would rival the image itself)
+          if (early_h_out && early_used && !*early_used && fp.n_local_tiles <= tiles_per_batch && d_out && !fp.packed &&
+              known_prev <= (uint64_t)n_acc) {
             // everything but the tail phase is in the accumulator: send the image now, patch it afterwards
             launch_resolve(accum, n_acc, fp.spp, d_out, st);
             ++launches;
