@@ -234,7 +234,8 @@ int nrb_scene_set_stream(NrbScene *scene, void *cuda_stream);
 /* Replaces scene::render (src/scene.rs:29-116).  `out_rgb` is a HOST buffer of
  * width*height*3 floats, row-major, pixel (x,y) at 3*(x + y*width) — the layout of
  * Image.pixels (src/image.rs:12-24).  Synchronous: the image is complete on return.
- * `stats` may be NULL. */
+ * `stats` may be NULL.  If `out_rgb` is pinned (nrb_host_alloc / cudaHostAlloc), the device->host copy of the
+ * image overlaps the last phase of the frame instead of following it. */
 int nrb_render(NrbScene *scene, const NrbCamera *camera, float *out_rgb, NrbStats *stats);
 
 /* Same render, result left in DEVICE memory (`d_out_rgb`, same layout) on the scene's
