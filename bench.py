@@ -10,7 +10,8 @@ tile-sharded over the ranks and collected by one NCCL all-gather -> strong scali
 
   value     whole-job Mrays/s with everything resident in HBM (nrb_render_device / tiles+gather)
   e2e       same metric through the host-facing C-ABI call nrb_render: camera arguments in, image
-            copied back to pinned host memory inside the timed region
+            copied back to pinned host memory inside the timed region (nrb_render starts that copy when
+            the frame enters its tail phase and patches the pixels the tail changes afterwards)
   roofline  dominant kernel's algorithmic bytes / CUDA-event launch time vs the measured HBM peak
   cpu_baseline / --impl reference
             the CPU oracle (C++ restatement of the reference path; the Rust reference itself cannot
