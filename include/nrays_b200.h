@@ -265,6 +265,13 @@ int nrb_ipc_open(int device, const NrbIpcHandle *handle, void **d_ptr);         
 int nrb_ipc_close(int device, void *d_ptr);
 int nrb_ipc_free(int device, void *d_ptr);
 
+/* Pins and maps caller-owned host memory and returns the address kernels use for it.  With a POSIX shared-memory
+ * segment that every rank of the node maps, nrb_render_tiles_to_image(.., d_ptr, ..) makes each rank's resolve kernel
+ * store its finished tiles straight into the ONE host image over its own PCIe link: the final destination of
+ * scene::render (a host Image) is reached without passing through another GPU. */
+int nrb_host_register(int device, void *host_ptr, uint64_t bytes, void **d_ptr);
+int nrb_host_unregister(int device, void *host_ptr);
+
 /* Number of 16x16 tiles covering width x height, and how many of them a tile set owns. */
 uint32_t nrb_tile_count(uint32_t width, uint32_t height);
 uint32_t nrb_tile_count_local(uint32_t width, uint32_t height, const NrbTileSet *tiles);

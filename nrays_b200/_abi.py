@@ -207,6 +207,8 @@ EXPORTS = [
     "nrb_ipc_open",
     "nrb_ipc_close",
     "nrb_ipc_free",
+    "nrb_host_register",
+    "nrb_host_unregister",
     "nrb_tile_count",
     "nrb_tile_count_local",
     "nrb_untile_device",

@@ -60,6 +60,10 @@ def load():
     lib.nrb_ipc_close.restype = C.c_int
     lib.nrb_ipc_free.argtypes = [C.c_int, vp]
     lib.nrb_ipc_free.restype = C.c_int
+    lib.nrb_host_register.argtypes = [C.c_int, vp, C.c_uint64, C.POINTER(vp)]
+    lib.nrb_host_register.restype = C.c_int
+    lib.nrb_host_unregister.argtypes = [C.c_int, vp]
+    lib.nrb_host_unregister.restype = C.c_int
     lib.nrb_tile_count.argtypes = [u32, u32]
     lib.nrb_tile_count.restype = u32
     lib.nrb_tile_count_local.argtypes = [u32, u32, C.POINTER(A.NrbTileSet)]

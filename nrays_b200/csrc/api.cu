@@ -1340,6 +1340,32 @@ int nrb_ipc_free(int device, void *d_ptr) {
   return NRB_OK;
 }
 
+int nrb_host_register(int device, void *host_ptr, uint64_t bytes, void **d_ptr) {
+  if (!host_ptr || !d_ptr || bytes == 0) return fail(NRB_ERR_INVALID_ARG, "host_register: bad arguments");
+  CU(cudaSetDevice(device));
+  cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(NRB_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+  }
+  void *dp = nullptr;
+  e = cudaHostGetDevicePointer(&dp, host_ptr, 0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cudaHostUnregister(host_ptr);
+    return fail(NRB_ERR_CUDA, std::string("cudaHostGetDevicePointer: ") + cudaGetErrorString(e));
+  }
+  *d_ptr = dp;
+  return NRB_OK;
+}
+
+int nrb_host_unregister(int device, void *host_ptr) {
+  if (!host_ptr) return NRB_OK;
+  CU(cudaSetDevice(device));
+  CU(cudaHostUnregister(host_ptr));
+  return NRB_OK;
+}
+
 uint32_t nrb_tile_count(uint32_t width, uint32_t height) {
   return ((width + NRB_TILE - 1) / NRB_TILE) * ((height + NRB_TILE - 1) / NRB_TILE);
 }

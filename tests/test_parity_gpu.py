@@ -250,6 +250,34 @@ def test_rgb8_output_is_the_png_quantisation(gpu):
     scene.close()
 
 
+def test_tiles_resolved_into_registered_host_memory(gpu):
+    """nrb_host_register maps caller-owned host memory (in production: a shared-memory segment all ranks map); the
+    resolve kernels of all (virtual) ranks store their tiles straight into that host image."""
+    import mmap
+
+    from nrays_b200 import dist
+
+    scene, camd, cfg = configs.build("C3", target_tris=30000, lod=4)
+    w, h, world = 176, 100, 4
+    cam = make_camera(w, h, 2, 1.0, camd.eye, camd.projection((w, h)), seed=9)
+    full = np.empty(w * h * 3, np.float32)
+    _lib.check(gpu.nrb_render(scene.handle, C.byref(cam), full.ctypes.data_as(C.POINTER(C.c_float)), None))
+    buf = mmap.mmap(-1, w * h * 12)          # page-aligned anonymous mapping, like a shared-memory segment
+    host = np.frombuffer(buf, dtype=np.float32)
+    host[:] = -5.0
+    cbuf = C.c_char.from_buffer(buf)
+    dptr = C.c_void_p()
+    _lib.check(gpu.nrb_host_register(0, C.c_void_p(C.addressof(cbuf)), w * h * 12, C.byref(dptr)))
+    for r in range(world):
+        dist.render_tiles_to_image(scene, cam, r, world, dptr)
+    np.testing.assert_allclose(host, full, rtol=0, atol=3e-5)
+    _lib.check(gpu.nrb_host_unregister(0, C.c_void_p(C.addressof(cbuf))))
+    assert gpu.nrb_host_register(0, None, 16, C.byref(dptr)) == A.NRB_ERR_INVALID_ARG
+    del host, cbuf
+    buf.close()
+    scene.close()
+
+
 def test_pinned_destination_overlaps_the_copy_and_patches_the_tail(gpu):
     """nrb_render into PINNED host memory starts the image's device->host copy when the frame enters its tail phase and
     then stores the pixels the tail changed straight into the (mapped) host image; the result is the image of the plain path."""
