@@ -213,18 +213,6 @@ def run_ours(args, rank, local_rank, world):
     host_img = np.ctypeslib.as_array(C.cast(host_ptr, C.POINTER(C.c_float)), shape=(h * w * 3,))
     pinned_t = torch.empty(h * w * 3, dtype=torch.float32).pin_memory() if world > 1 else None
 
-    # End-to-end at N > 1: the destination of scene::render is a HOST image, so every rank's resolve kernel stores its
-    # tiles straight into one shared, pinned host image over its own PCIe link (dist.SharedHostImage); fallback: the
-    # device image on rank 0 + one device->host copy of the whole frame.
-    shost = None
-    if world > 1 and os.environ.get("NRB_BENCH_E2E", "shared") == "shared":
-        try:
-            shost = dist.SharedHostImage(w, h, rank, world, local_rank)
-        except Exception as e:
-            if rank == 0:
-                print("bench: shared host image unavailable (%s), e2e copies the frame from rank 0" % e, file=sys.stderr)
-            shost = None
-
     def cam_for(step):
         return make_camera(w, h, spp, window, camdesc.eye, proj, seed=step)
 
@@ -248,10 +236,6 @@ def run_ours(args, rank, local_rank, world):
         if world == 1:
             st = A.NrbStats()
             _lib.check(lib.nrb_render(scene.handle, C.byref(cam), C.cast(host_ptr, C.POINTER(C.c_float)), C.byref(st)))
-            return st, 0
-        if shost is not None:
-            st = dist.render_tiles_to_image(scene, cam, rank, world, shost.dev_ptr)
-            shost.sync()   # every rank's stores have landed in the host image when this all-reduce completes
             return st, 0
         st, extra = step_device(step)
         if rank == 0:
@@ -291,12 +275,6 @@ def run_ours(args, rank, local_rank, world):
             dist.render_device(scene, cam_for(999), ref_img)
             verified = bool((out - ref_img).abs().max().item() < 1e-4)
         barrier()
-        if shost is not None:
-            step_e2e(999)
-            barrier()
-            if rank == 0:
-                verified = verified and bool(np.abs(shost.array - ref_img.cpu().numpy()).max() < 1e-4)
-            barrier()
     for i in range(max(1, min(args.warmup, 2))):
         step_e2e(2000 + i)
 
@@ -396,8 +374,7 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": rays_e2e / (ms_e2e_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(A.NrbCamera) * world,
                     "d2h_bytes_per_step": w * h * 3 * 4, "ms_per_step": ms_e2e_max / args.steps,
                     "path": ("nrb_render into pinned host memory" if world == 1 else
-                             ("every rank's resolve kernel stores its tiles into one shared pinned host image (its own PCIe link)"
-                              if shost is not None else "device image on rank 0, then one device->host copy"))},
+                             "device image on rank 0, then one device->host copy of the frame")},
             "gpu_launches": int(lt.item()),
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -405,9 +382,6 @@ def run_ours(args, rank, local_rank, world):
         }
         print(json.dumps(line), flush=True)
     lib.nrb_host_free(host_ptr)
-    if shost is not None:
-        barrier()
-        shost.close()
     if peer is not None:
         out = None
         barrier()

@@ -185,64 +185,3 @@ def render_tiles_to_image(scene, cam, rank, world, image_ptr):
     _lib.check(_lib.load().nrb_render_tiles_to_image(scene.handle, C.byref(cam), C.byref(ts), ptr, C.byref(stats)))
     return stats
 
-
-class SharedHostImage:
-    """Row-major W*H*3 float image in POSIX shared memory, mapped by every rank of the node and registered with CUDA
-    (pinned + device-mapped) in each process: `render_tiles_to_image(.., self.dev_ptr)` makes every rank's resolve kernel
-    store its finished tiles straight into the ONE host image over its own PCIe link.  This is the end-to-end form of the
-    exchange: the destination of scene::render is a host Image, and N ranks fill it through N links in parallel instead of
-    funnelling 25 MB through rank 0's single link.  Collective constructor (default process group); `array` is the numpy
-    view every rank can read after `sync()`."""
-
-    def __init__(self, width, height, rank, world, device):
-        import torch
-        import torch.distributed as td
-        from multiprocessing import shared_memory
-
-        from . import _lib
-
-        self.lib, self.rank, self.world, self.device = _lib.load(), rank, world, int(device)
-        self.nbytes = width * height * 3 * 4
-        self.shm, self.dev_ptr, self._registered = None, C.c_void_p(), False
-        name = [None]
-        if rank == 0:
-            self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
-            name[0] = self.shm.name
-        td.broadcast_object_list(name, src=0)
-        ok = True
-        try:
-            if rank != 0:
-                self.shm = shared_memory.SharedMemory(name=name[0])
-            self.array = np.ndarray((width * height * 3,), dtype=np.float32, buffer=self.shm.buf)
-            self._cbuf = C.c_char.from_buffer(self.shm.buf)
-            self._addr = C.addressof(self._cbuf)
-            ok = self.lib.nrb_host_register(self.device, C.c_void_p(self._addr), self.nbytes, C.byref(self.dev_ptr)) == A.NRB_OK
-            self._registered = ok
-        except Exception:
-            ok = False
-        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda:%d" % self.device)
-        td.all_reduce(flag, op=td.ReduceOp.MIN)
-        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.device)
-        if int(flag.item()) == 0:
-            self.close()
-            raise RuntimeError("SharedHostImage: shared memory / cudaHostRegister failed on some rank")
-
-    def sync(self):
-        import torch.distributed as td
-
-        td.all_reduce(self._flag)
-
-    def close(self):
-        if self._registered:
-            self.lib.nrb_host_unregister(self.device, C.c_void_p(self._addr))
-            self._registered = False
-        if self.shm is not None:
-            self.array = None
-            self._cbuf = None
-            try:
-                self.shm.close()
-                if self.rank == 0:
-                    self.shm.unlink()
-            except Exception:
-                pass
-            self.shm = None
