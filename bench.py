@@ -281,7 +281,7 @@ def run_ours(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.15)
+        time.sleep(0.4)   # let nvidia-smi start sampling before the timed regions
     ms_dev, stats_dev = timed(step_device, args.steps, 0)
     ms_e2e, stats_e2e = timed(step_e2e, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None   # sampled across both timed regions
