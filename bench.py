@@ -213,6 +213,18 @@ def run_ours(args, rank, local_rank, world):
     host_img = np.ctypeslib.as_array(C.cast(host_ptr, C.POINTER(C.c_float)), shape=(h * w * 3,))
     pinned_t = torch.empty(h * w * 3, dtype=torch.float32).pin_memory() if world > 1 else None
 
+    # End-to-end at N > 1: the destination of scene::render is a HOST image; every rank DMAs its tile columns straight into
+    # one shared pinned host image over its own PCIe link (dist.SharedHostImage + nrb_render_tiles_to_host).  Fallback:
+    # the device image on rank 0 + one device->host copy of the whole frame.
+    shost = None
+    if world > 1 and os.environ.get("NRB_BENCH_E2E", "shared") == "shared" and w % 16 == 0 and (w // 16) % world == 0:
+        try:
+            shost = dist.SharedHostImage(w, h, rank, world, local_rank)
+        except Exception as e:
+            if rank == 0:
+                print("bench: shared host image unavailable (%s), e2e copies the frame from rank 0" % e, file=sys.stderr)
+            shost = None
+
     def cam_for(step):
         return make_camera(w, h, spp, window, camdesc.eye, proj, seed=step)
 
@@ -236,6 +248,10 @@ def run_ours(args, rank, local_rank, world):
         if world == 1:
             st = A.NrbStats()
             _lib.check(lib.nrb_render(scene.handle, C.byref(cam), C.cast(host_ptr, C.POINTER(C.c_float)), C.byref(st)))
+            return st, 0
+        if shost is not None:
+            st = dist.render_tiles_to_host(scene, cam, rank, world, shost.addr)
+            shost.sync()   # every rank's DMA has landed in the host image when this all-reduce completes
             return st, 0
         st, extra = step_device(step)
         if rank == 0:
@@ -275,6 +291,22 @@ def run_ours(args, rank, local_rank, world):
             dist.render_device(scene, cam_for(999), ref_img)
             verified = bool((out - ref_img).abs().max().item() < 1e-4)
         barrier()
+        if shost is not None:
+            # the shared host image must hold the same frame; if it does not, every rank drops back to the copy path
+            ok_t = torch.ones(1, dtype=torch.int32, device=dev)
+            try:
+                step_e2e(999)
+                barrier()
+                if rank == 0 and not bool(np.abs(shost.array - ref_img.cpu().numpy()).max() < 1e-4):
+                    ok_t.zero_()
+            except Exception as e:
+                print("bench: rank %d: shared host image path failed (%s)" % (rank, e), file=sys.stderr)
+                ok_t.zero_()
+            td.all_reduce(ok_t, op=td.ReduceOp.MIN)
+            if int(ok_t.item()) == 0:
+                shost.close()
+                shost = None
+            barrier()
     for i in range(max(1, min(args.warmup, 2))):
         step_e2e(2000 + i)
 
@@ -374,7 +406,8 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": rays_e2e / (ms_e2e_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(A.NrbCamera) * world,
                     "d2h_bytes_per_step": w * h * 3 * 4, "ms_per_step": ms_e2e_max / args.steps,
                     "path": ("nrb_render into pinned host memory" if world == 1 else
-                             "device image on rank 0, then one device->host copy of the frame")},
+                             ("every rank DMAs its tile columns into one shared pinned host image over its own PCIe link"
+                              if shost is not None else "device image on rank 0, then one device->host copy of the frame"))},
             "gpu_launches": int(lt.item()),
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -382,6 +415,9 @@ def run_ours(args, rank, local_rank, world):
         }
         print(json.dumps(line), flush=True)
     lib.nrb_host_free(host_ptr)
+    if shost is not None:
+        barrier()
+        shost.close()
     if peer is not None:
         out = None
         barrier()

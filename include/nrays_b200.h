@@ -255,6 +255,14 @@ int nrb_render_tiles_device(NrbScene *scene, const NrbCamera *camera, const NrbT
 int nrb_render_tiles_to_image(NrbScene *scene, const NrbCamera *camera, const NrbTileSet *tiles, float *d_image_rgb,
                               NrbStats *stats);
 
+/* End-to-end form of the same exchange: the destination of scene::render is a HOST image.  Renders this rank's tiles and
+ * drops them into `host_image_rgb` — pinned / registered host memory (nrb_host_register), e.g. one shared-memory segment
+ * mapped by every rank — with ONE strided 2-D DMA over this GPU's own PCIe link; N ranks fill the image through N links in
+ * parallel.  Needs width % 16 == 0, tiles_x % stride == 0 and first < stride (each rank then owns whole tile columns);
+ * otherwise NRB_ERR_UNSUPPORTED and the caller uses nrb_render_tiles_to_image. */
+int nrb_render_tiles_to_host(NrbScene *scene, const NrbCamera *camera, const NrbTileSet *tiles, float *host_image_rgb,
+                             NrbStats *stats);
+
 /* Device memory that other processes on the node can map (one process per GPU): the owner allocates and
  * passes the 64-byte handle around (any transport), peers open it and get a pointer valid in their kernels. */
 typedef struct NrbIpcHandle {
@@ -265,10 +273,9 @@ int nrb_ipc_open(int device, const NrbIpcHandle *handle, void **d_ptr);         
 int nrb_ipc_close(int device, void *d_ptr);
 int nrb_ipc_free(int device, void *d_ptr);
 
-/* Pins and maps caller-owned host memory (so nrb_render can overlap its copy, and kernels can store into it) and
- * returns the address kernels use for it.  Measured: letting every rank's resolve kernel store its tiles straight
- * into one shared host image (nrb_render_tiles_to_image with such a pointer) is correct but slower than the device
- * image + one DMA (kernel stores over PCIe reach ~10 GB/s): 2.65 vs 1.87 ms per C3 frame at 2 GPUs. */
+/* Pins and maps caller-owned host memory (a shared-memory segment for nrb_render_tiles_to_host; any buffer nrb_render
+ * should overlap its copy into) and returns the address kernels use for it.  (Kernel stores into such memory work —
+ * nrb_render_tiles_to_image accepts the pointer — but reach only ~10 GB/s over PCIe; DMA is the way in.) */
 int nrb_host_register(int device, void *host_ptr, uint64_t bytes, void **d_ptr);
 int nrb_host_unregister(int device, void *host_ptr);
 

@@ -203,6 +203,7 @@ EXPORTS = [
     "nrb_render_device",
     "nrb_render_tiles_device",
     "nrb_render_tiles_to_image",
+    "nrb_render_tiles_to_host",
     "nrb_ipc_alloc",
     "nrb_ipc_open",
     "nrb_ipc_close",

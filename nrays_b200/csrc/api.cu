@@ -778,7 +778,7 @@ cudaEvent_t get_event(NrbScene &S, size_t &used) {
 // changed straight into the host image once that copy has landed.  *early_used tells the caller which happened.
 int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, float *d_out, uint8_t *d_out8,
                   uint32_t *n_local_tiles, NrbStats *stats, bool to_image = false, float *early_h_out = nullptr,
-                  float *early_d_out = nullptr, bool *early_used = nullptr) {
+                  float *early_d_out = nullptr, bool *early_used = nullptr, float *segments_h_out = nullptr) {
   CU(cudaSetDevice(S.device));
   FrameParams fp;
   int rc = make_frame_params(cam, tiles, fp);
@@ -1040,7 +1040,14 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
     launch_patch_host_image(accum, d_out, n_acc, fp.spp, early_d_out, st);
   } else if (d_out8)
     launch_resolve_rgb8(accum, n_acc, fp.spp, d_out8, st);
-  else if (to_image && fp.packed)
+  else if (segments_h_out && fp.packed) {
+    // this rank's tile columns as back-to-back 192-byte segments, then ONE strided 2-D DMA into the shared host image
+    const uint32_t cols_per_rank = fp.tiles_x / fp.tile_stride;
+    launch_resolve_tiles_to_segments(accum, fp, cols_per_rank, d_out, st);
+    const size_t seg = (size_t)NRB_TILE * 3 * sizeof(float);
+    CU(cudaMemcpy2DAsync((char *)segments_h_out + (size_t)fp.tile_first * seg, (size_t)fp.tile_stride * seg, d_out, seg, seg,
+                         (size_t)fp.height * cols_per_rank, cudaMemcpyDeviceToHost, st));
+  } else if (to_image && fp.packed)
     launch_resolve_tiles_to_image(accum, fp, d_out, st);
   else
     launch_resolve(accum, n_acc, fp.spp, d_out, st);
@@ -1291,6 +1298,21 @@ int nrb_render_tiles_to_image(NrbScene *scene, const NrbCamera *camera, const Nr
                               NrbStats *stats) {
   if (!scene || !camera || !tiles || !d_image_rgb) return fail(NRB_ERR_INVALID_ARG, "scene/camera/tiles/image is NULL");
   return render_device(*scene, *camera, tiles, d_image_rgb, nullptr, nullptr, stats, true);
+}
+
+int nrb_render_tiles_to_host(NrbScene *scene, const NrbCamera *camera, const NrbTileSet *tiles, float *host_image_rgb,
+                             NrbStats *stats) {
+  if (!scene || !camera || !tiles || !host_image_rgb) return fail(NRB_ERR_INVALID_ARG, "scene/camera/tiles/image is NULL");
+  const uint32_t tiles_x = (camera->width + NRB_TILE - 1) / NRB_TILE;
+  if (tiles->stride == 0 || tiles->first >= tiles->stride || camera->width % NRB_TILE != 0 || tiles_x % tiles->stride != 0)
+    return fail(NRB_ERR_UNSUPPORTED, "tiles_to_host needs width % 16 == 0, tiles_x % stride == 0 and first < stride "
+                                     "(each rank then owns whole tile columns); use nrb_render_tiles_to_image");
+  CU(cudaSetDevice(scene->device));
+  const uint32_t tiles_y = (camera->height + NRB_TILE - 1) / NRB_TILE;
+  const size_t local_px = (size_t)(tiles_x / tiles->stride) * tiles_y * NRB_TILE * NRB_TILE;
+  CU(scene->d_out.ensure(std::max<size_t>(local_px * 3 * sizeof(float), 16)));
+  return render_device(*scene, *camera, tiles, scene->d_out.as<float>(), nullptr, nullptr, stats, false, nullptr, nullptr, nullptr,
+                       host_image_rgb);
 }
 
 int nrb_ipc_alloc(int device, uint64_t bytes, void **d_ptr, NrbIpcHandle *handle) {

@@ -1308,6 +1308,28 @@ __global__ void resolve_tiles_to_image_kernel(const float4 *accum, FrameParams f
   }
 }
 
+// End-to-end form of the exchange (nrb_render_tiles_to_host): when tiles_x is a multiple of the rank count, rank r owns
+// whole tile COLUMNS r, r + N, ...; in the row-major image its pixels are 16-pixel (192-byte) segments at pitch
+// N * 192 bytes.  This kernel resolves the rank's tiles into a staging buffer holding exactly those segments back to
+// back — segment j = y * columns_per_rank + k — so ONE strided 2-D DMA drops them into the shared host image.
+__global__ void resolve_tiles_to_segments_kernel(const float4 *accum, FrameParams fp, float inv_spp, uint32_t cols_per_rank, float *stage) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread = four pixels of one tile row
+  if (t >= fp.n_local_tiles * (NRB_TILE * NRB_TILE / 4u)) return;
+  const uint32_t lt = t / (NRB_TILE * NRB_TILE / 4u), r = t % (NRB_TILE * NRB_TILE / 4u);
+  const uint32_t row = r / (NRB_TILE / 4u), x4 = (r % (NRB_TILE / 4u)) * 4u;
+  const uint32_t tile = fp.tile_first + lt * fp.tile_stride;
+  const uint32_t ty = fdiv(tile, fp.div_tiles_x), tx = tile - ty * fp.tiles_x;
+  const uint32_t y = ty * NRB_TILE + row;
+  if (y >= fp.height) return;
+  const uint32_t k = fdiv(tx - fp.tile_first, fp.div_tile_stride);  // tile_first < tile_stride: the rank's k-th column
+  const float4 *src = accum + (size_t)lt * (NRB_TILE * NRB_TILE) + row * NRB_TILE + x4;
+  float4 *dst = reinterpret_cast<float4 *>(stage + ((size_t)(y * cols_per_rank + k) * NRB_TILE + x4) * 3u);
+  const float4 a = src[0], b = src[1], c = src[2], d = src[3];
+  dst[0] = make_float4(a.x * inv_spp, a.y * inv_spp, a.z * inv_spp, b.x * inv_spp);
+  dst[1] = make_float4(b.y * inv_spp, b.z * inv_spp, c.x * inv_spp, c.y * inv_spp);
+  dst[2] = make_float4(c.z * inv_spp, d.x * inv_spp, d.y * inv_spp, d.z * inv_spp);
+}
+
 // K6 — packed tiles of n_ranks ranks (rank r owns tiles r, r+n_ranks, ...) -> row-major image
 __global__ void untile_kernel(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width,
                               uint32_t height, uint32_t tiles_x, float *out_rgb) {
@@ -1408,6 +1430,12 @@ void launch_resolve_tiles_to_image(const float4 *accum, const FrameParams &fp, f
   const uint32_t n = fp.n_local_tiles * (NRB_TILE * NRB_TILE / 4u);
   if (!n) return;
   resolve_tiles_to_image_kernel<<<(n + 255) / 256, 256, 0, st>>>(accum, fp, 1.0f / (float)fp.spp, out_rgb);
+}
+
+void launch_resolve_tiles_to_segments(const float4 *accum, const FrameParams &fp, uint32_t cols_per_rank, float *stage, cudaStream_t st) {
+  const uint32_t n = fp.n_local_tiles * (NRB_TILE * NRB_TILE / 4u);
+  if (!n) return;
+  resolve_tiles_to_segments_kernel<<<(n + 255) / 256, 256, 0, st>>>(accum, fp, 1.0f / (float)fp.spp, cols_per_rank, stage);
 }
 
 void launch_untile(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width, uint32_t height,

@@ -55,6 +55,7 @@ void launch_resolve(const float4 *accum, uint32_t n, uint32_t spp, float *out_rg
 void launch_resolve_rgb8(const float4 *accum, uint32_t n, uint32_t spp, uint8_t *out, cudaStream_t st);
 void launch_patch_host_image(const float4 *accum, const float *early_rgb, uint32_t n, uint32_t spp, float *host_rgb, cudaStream_t st);
 void launch_resolve_tiles_to_image(const float4 *accum, const FrameParams &fp, float *out_rgb, cudaStream_t st);
+void launch_resolve_tiles_to_segments(const float4 *accum, const FrameParams &fp, uint32_t cols_per_rank, float *stage, cudaStream_t st);
 void launch_untile(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width, uint32_t height,
                    float *out_rgb, cudaStream_t st);
 int trace_blocks_per_sm(bool has_shapes);

@@ -185,3 +185,78 @@ def render_tiles_to_image(scene, cam, rank, world, image_ptr):
     _lib.check(_lib.load().nrb_render_tiles_to_image(scene.handle, C.byref(cam), C.byref(ts), ptr, C.byref(stats)))
     return stats
 
+
+
+# ---- end-to-end exchange: N ranks fill ONE shared pinned host image through their own PCIe links ------------------
+class SharedHostImage:
+    """Row-major W*H*3 float image in POSIX shared memory, mapped by every rank of the node and registered with CUDA in
+    each process (nrb_host_register).  `render_tiles_to_host` drops each rank's tile columns into it with one strided 2-D
+    DMA, so the host image — the thing scene::render returns — is filled through N PCIe links in parallel instead of
+    25 MB funnelling through rank 0's link.  Collective constructor (default process group); after `sync()` every rank can
+    read `array`."""
+
+    def __init__(self, width, height, rank, world, device):
+        import torch
+        import torch.distributed as td
+        from multiprocessing import shared_memory
+
+        from . import _lib
+
+        self.lib, self.rank, self.world, self.device = _lib.load(), rank, world, int(device)
+        self.nbytes = width * height * 3 * 4
+        self.shm, self.array, self._cbuf, self._registered, self.addr = None, None, None, False, 0
+        name = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
+            name[0] = self.shm.name
+        td.broadcast_object_list(name, src=0)
+        ok = True
+        try:
+            if rank != 0:
+                self.shm = shared_memory.SharedMemory(name=name[0])
+            self.array = np.ndarray((width * height * 3,), dtype=np.float32, buffer=self.shm.buf)
+            self._cbuf = C.c_char.from_buffer(self.shm.buf)
+            self.addr = C.addressof(self._cbuf)
+            dptr = C.c_void_p()
+            ok = self.lib.nrb_host_register(self.device, C.c_void_p(self.addr), self.nbytes, C.byref(dptr)) == A.NRB_OK
+            self._registered = ok
+        except Exception:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda:%d" % self.device)
+        td.all_reduce(flag, op=td.ReduceOp.MIN)
+        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.device)
+        if int(flag.item()) == 0:
+            self.close()
+            raise RuntimeError("SharedHostImage: shared memory / cudaHostRegister failed on some rank")
+
+    def sync(self):
+        """All ranks' DMAs have landed when this all-reduce completes (each rank's render call returns after its own)."""
+        import torch.distributed as td
+
+        td.all_reduce(self._flag)
+
+    def close(self):
+        if self._registered:
+            self.lib.nrb_host_unregister(self.device, C.c_void_p(self.addr))
+            self._registered = False
+        self.array = None
+        self._cbuf = None
+        if self.shm is not None:
+            try:
+                self.shm.close()
+                if self.rank == 0:
+                    self.shm.unlink()
+            except Exception:
+                pass
+            self.shm = None
+
+
+def render_tiles_to_host(scene, cam, rank, world, host_addr):
+    """Render this rank's tile columns and DMA them into the row-major HOST image at `host_addr` (registered memory).
+    Raises NraysError(NRB_ERR_UNSUPPORTED) when the frame geometry does not give every rank whole tile columns."""
+    from . import _lib
+
+    ts = A.NrbTileSet(rank, world)
+    stats = A.NrbStats()
+    _lib.check(_lib.load().nrb_render_tiles_to_host(scene.handle, C.byref(cam), C.byref(ts), C.c_void_p(int(host_addr)), C.byref(stats)))
+    return stats

@@ -258,7 +258,7 @@ def test_tiles_resolved_into_registered_host_memory(gpu):
     from nrays_b200 import dist
 
     scene, camd, cfg = configs.build("C3", target_tris=30000, lod=4)
-    w, h, world = 176, 100, 4
+    w, h, world = 192, 100, 4       # 12 tile columns: 3 per rank; the last tile row is ragged (100 = 6 * 16 + 4)
     cam = make_camera(w, h, 2, 1.0, camd.eye, camd.projection((w, h)), seed=9)
     full = np.empty(w * h * 3, np.float32)
     _lib.check(gpu.nrb_render(scene.handle, C.byref(cam), full.ctypes.data_as(C.POINTER(C.c_float)), None))
@@ -271,6 +271,13 @@ def test_tiles_resolved_into_registered_host_memory(gpu):
     for r in range(world):
         dist.render_tiles_to_image(scene, cam, r, world, dptr)
     np.testing.assert_allclose(host, full, rtol=0, atol=3e-5)
+    # the DMA form: each (virtual) rank drops its tile columns into the host image with one strided 2-D copy
+    host[:] = -6.0
+    for r in range(world):
+        dist.render_tiles_to_host(scene, cam, r, world, C.addressof(cbuf))
+    np.testing.assert_allclose(host, full, rtol=0, atol=3e-5)
+    ts = A.NrbTileSet(0, 5)        # 12 tile columns do not split over 5 ranks: the caller must use the other exchange
+    assert gpu.nrb_render_tiles_to_host(scene.handle, C.byref(cam), C.byref(ts), C.c_void_p(C.addressof(cbuf)), None) == A.NRB_ERR_UNSUPPORTED
     _lib.check(gpu.nrb_host_unregister(0, C.c_void_p(C.addressof(cbuf))))
     assert gpu.nrb_host_register(0, None, 16, C.byref(dptr)) == A.NRB_ERR_INVALID_ARG
     del host, cbuf
