@@ -214,6 +214,12 @@ class SharedHostImage:
         try:
             if rank != 0:
                 self.shm = shared_memory.SharedMemory(name=name[0])
+                try:  # only the owner unlinks the segment; keep this process's resource tracker out of it
+                    from multiprocessing import resource_tracker
+
+                    resource_tracker.unregister(self.shm._name, "shared_memory")
+                except Exception:
+                    pass
             self.array = np.ndarray((width * height * 3,), dtype=np.float32, buffer=self.shm.buf)
             self._cbuf = C.c_char.from_buffer(self.shm.buf)
             self.addr = C.addressof(self._cbuf)
