@@ -254,9 +254,8 @@ def test_trace_matches_brute_force(seed):
     assert compared > 0.9 * w * h
 
 
-def test_render_counts_and_image_match_brute_force():
-    """nro_render (scene::render restated) against the brute force on a fixed scene with every ray class: image and the
-    per-class ray counts (reflect / refract / shadow) — also checks the flatten step, which only the oracle goes through."""
+def fixed_scene():
+    """A scene with every ray class (textured reflective floor, refractive box, reflective ball, cone, two lights)."""
     rng = np.random.default_rng(77)
     P, Fc = np.array([[-3, -1, -3], [3, -1, -3], [3, -1, 3], [-3, -1, 3]], np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
     UV = np.array([[0, 0], [2, 0], [2, 2], [0, 2]], np.float32)
@@ -269,20 +268,54 @@ def test_render_counts_and_image_match_brute_force():
                      Isometry3.new((-1.0, 0.0, 0.5), (0, 0, 0)), Ball(0.9))
     cone = SceneNode(NormalMaterial(), 0, 0, 1.0, 1.0, Isometry3.new((0.0, -0.2, 1.8), (0.0, 0.0, 0.3)), Cone(0.8, 0.6))
     nodes, lights = [floor, glass, ball, cone], [Light((2, 5, -3), 0.0, 1, (1, 1, 1)), Light((-4, 3, -2), 0.0, 4, (0.4, 0.4, 0.6))]
-    sc = Scene(nodes, lights, (0.3, 0.5, 0.9), upload=False)
-    w, h = 24, 16
-    eye = (0.0, 1.5, -6.0)
-    proj = camera_projection(eye, (0, 0, 0), 45.0, w, h)
-    cam = make_camera(w, h, 1, 0.0, eye, proj, seed=0, max_depth=8)
-    img, st = O.OracleScene(sc.flat, 64).render(cam, threads=2)
-    bs = BF.BruteScene(nodes, lights, (0.3, 0.5, 0.9), max_depth=8)
+    return nodes, lights, (0.3, 0.5, 0.9), (0.0, 1.5, -6.0)
+
+
+def brute_image(nodes, lights, background, eye, w, h, max_depth=8, fovy=45.0):
+    proj = camera_projection(eye, (0, 0, 0), fovy, w, h)
+    bs = BF.BruteScene(nodes, lights, background, max_depth=max_depth)
     want = np.zeros((w * h, 3), np.float32)
     for y in range(h):
         for x in range(w):
             want[y * w + x] = bs.trace(*BF.primary_ray(w, h, eye, proj, x, y))
+    return want, bs, proj
+
+
+def test_render_counts_and_image_match_brute_force():
+    """nro_render (scene::render restated) against the brute force on a fixed scene with every ray class: image and the
+    per-class ray counts (reflect / refract / shadow) — also checks the flatten step, which only the oracle goes through."""
+    nodes, lights, bg, eye = fixed_scene()
+    sc = Scene(nodes, lights, bg, upload=False)
+    w, h = 24, 16
+    want, bs, proj = brute_image(nodes, lights, bg, eye, w, h)
+    cam = make_camera(w, h, 1, 0.0, eye, proj, seed=0, max_depth=8)
+    img, st = O.OracleScene(sc.flat, 64).render(cam, threads=2)
     assert bs.min_gap > 1e-7
     assert np.abs(img - want).max() < 5e-5
     assert st.rays_primary == w * h
     assert (st.rays_reflect, st.rays_refract, st.rays_shadow, st.paths_truncated) == (
         bs.counts["reflect"], bs.counts["refract"], bs.counts["shadow"], bs.counts["truncated"])
     assert st.rays_reflect > 0 and st.rays_refract > 0 and st.rays_shadow > 0
+
+
+@pytest.mark.gpu
+def test_device_matches_brute_force_directly(gpu):
+    """The CUDA path against the brute-force checker with NO oracle in between: the fixed every-ray-class scene and three
+    random scenes (RNG-free: window 0, point lights), through nrb_render."""
+    from nrays_b200 import render
+    from util import assert_parity
+
+    cases = [fixed_scene()]
+    for seed in (3001, 3004, 3006):
+        nodes, lights, rng = _rand_scene(seed)
+        cases.append((nodes, lights, (1.0, 1.0, 1.0), tuple(rng.uniform(-1, 1, 3) + np.array([0, 2.0, -9.0]))))
+    for k, (nodes, lights, bg, eye) in enumerate(cases):
+        w, h = 48, 32
+        want, bs, proj = brute_image(nodes, lights, bg, eye, w, h, max_depth=6, fovy=50.0)
+        scene = Scene(nodes, lights, bg)
+        img, st = render(scene, (w, h), 1, 0.0, eye, proj, seed=0, max_depth=6, return_stats=True)
+        scene.close()
+        assert_parity(img.pixels, want, what="device vs brute force #%d" % k, wh=(w, h))
+        for key, name in (("rays_reflect", "reflect"), ("rays_refract", "refract"), ("rays_shadow", "shadow")):
+            a, b = int(getattr(st, key)), bs.counts[name]
+            assert abs(a - b) <= max(4, 5e-3 * b), (k, key, a, b)

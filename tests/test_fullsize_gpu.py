@@ -6,7 +6,7 @@ import pytest
 
 import oracle_lib as O
 from nrays_b200 import _abi as A, _lib, configs, make_camera
-from util import TOL, image_metrics
+from util import MAX_FRAC_OVER, TOL, assert_parity, edge_flip_report, image_metrics
 
 pytestmark = pytest.mark.gpu
 
@@ -54,20 +54,54 @@ def test_c3_linearity_in_background(sponza):
     np.testing.assert_allclose(imgs[0.4], imgs[0.0] + 0.4 * (imgs[1.0] - imgs[0.0]), atol=2e-5)
 
 
-def test_c3_full_size_bands_against_oracle(sponza):
-    """A bounded sample of the full-size frame (3 bands x 6 rows, all 4 spp) against the f64 oracle."""
+def test_c3_full_frame_against_oracle(sponza):
+    """The WHOLE headline frame (1920x1080, 4 spp, jitter, 8.29 M primary rays) against the f64 oracle — not a sample."""
     lib, scene, camd, cfg = sponza
     w, h, spp = cfg["width"], cfg["height"], cfg["spp"]
     cam = make_camera(w, h, spp, cfg["window"], camd.eye, camd.projection((w, h)), seed=0)
-    img, _ = render_np(lib, scene, cam)
+    img, st = render_np(lib, scene, cam)
+    ref, ost = O.OracleScene(scene.flat, 64).render(cam)
+    assert_parity(img, ref, what="C3 full frame 1920x1080x4", wh=(w, h), max_frac=MAX_FRAC_OVER, mean_abs=2e-4)
+    assert st.rays_primary == ost.rays_primary
+    for k in ("rays_refract", "rays_shadow"):
+        a, b = int(getattr(st, k)), int(getattr(ost, k))
+        assert abs(a - b) <= 1e-3 * b, (k, a, b)
+
+
+def test_c5_tile_shard_bands_against_oracle(sponza):
+    """C5 (3840x2160, 16 spp) as ONE of eight tile shards (rank 3 owns tile columns 3, 11, 19, ...): three 16-row bands of
+    the pixels this rank owns against the f64 oracle at the full C5 camera — RNG keyed by the global pixel, so a shard's
+    pixels are the full frame's pixels."""
+    import torch
+
+    from nrays_b200 import dist
+
+    lib, scene, camd, cfg5 = sponza[0], sponza[1], sponza[2], configs.CONFIGS["C5"]
+    w, h, spp, world, rank = cfg5["width"], cfg5["height"], cfg5["spp"], 8, 3
+    cam = make_camera(w, h, spp, cfg5["window"], camd.eye, camd.projection((w, h)), seed=0)
+    img = torch.full((h * w * 3,), -1.0, dtype=torch.float32, device="cuda")
+    st = dist.render_tiles_to_image(scene, cam, rank, world, img.data_ptr())
+    torch.cuda.synchronize()
+    img = img.cpu().numpy().reshape(h, w, 3)
+    assert st.rays_primary == (w // 16 // world) * 16 * h * spp      # 30 of 240 tile columns, all rows
+    own = (np.arange(w) // 16) % world == rank
+    assert (img[:, ~own] == -1.0).all() and (img[:, own] >= 0.0).all()  # the shard wrote its tile columns and nothing else
     osc = O.OracleScene(scene.flat, 64)
-    ref = np.zeros_like(img)
-    rows = []
-    for y0 in (200, 540, 900):
-        osc.render(cam, 0, y0 * w, 6 * w, ref)
-        rows += list(range(y0 * w, (y0 + 6) * w))
-    m = image_metrics(img[rows], ref[rows])
-    assert m["frac_over"] <= 2e-3 and m["mean_abs"] < 2e-4, m
+    ref = np.zeros((h * w, 3), np.float32)
+    for y0 in (320, 1072, 1760):
+        osc.render(cam, 0, y0 * w, 16 * w, ref)
+        band_ref = ref.reshape(h, w, 3)[y0:y0 + 16][:, own]
+        band = img[y0:y0 + 16][:, own]
+        # own columns come in runs of 16 pixels: classify tile by tile width (16-wide strips glued side by side would put
+        # unrelated pixels next to each other), so use the plain fraction gate per band plus the classifier on each strip
+        m = image_metrics(band, band_ref)
+        over = 0
+        for k in range(band.shape[1] // 16):
+            r = edge_flip_report(band[:, 16 * k:16 * k + 16].reshape(-1, 3), band_ref[:, 16 * k:16 * k + 16].reshape(-1, 3), (16, 16))
+            assert r["unexplained"] == 0, ("C5 band %d strip %d" % (y0, k), r)
+            over += r["over"]
+        print("parity: C5 shard 3/8 band y0=%d: %r over=%d" % (y0, m, over))
+        assert m["frac_over"] <= 2 * MAX_FRAC_OVER and m["mean_abs"] < 2e-4, m
 
 
 def test_c2_full_size_against_oracle(gpu):
@@ -76,8 +110,7 @@ def test_c2_full_size_against_oracle(gpu):
     cam = make_camera(w, h, spp, cfg["window"], camd.eye, camd.projection((w, h)), seed=0)
     img, st = render_np(gpu, scene, cam)
     ref, ost = O.OracleScene(scene.flat, 64).render(cam)
-    m = image_metrics(img, ref)
-    assert m["frac_over"] <= 1e-3, m
+    assert_parity(img, ref, what="C2 full frame 1024x1024x4", wh=(w, h), max_frac=MAX_FRAC_OVER)
     assert st.rays_primary == ost.rays_primary == 4194304
     assert abs(int(st.rays_reflect) - int(ost.rays_reflect)) <= 2e-4 * ost.rays_reflect
     scene.close()
@@ -93,25 +126,24 @@ def test_c1_reference_config_against_oracle(gpu):
         cam = make_camera(256, 256, 1, 0.0, cams[0].eye, cams[0].projection((256, 256)), seed=0)
         img, st = render_np(gpu, scene, cam)
         ref, ost = O.OracleScene(scene.flat, 64).render(cam)
-        m = image_metrics(img, ref)
-        assert m["frac_over"] <= 1e-3, m
+        assert_parity(img, ref, what="C1 256x256x1 light radius %s" % radius, wh=(256, 256), max_frac=MAX_FRAC_OVER)
         assert abs(int(st.rays_reference) - int(ost.rays_reference)) <= 1e-3 * ost.rays_reference
         scene.close()
 
 
-def test_c4_hairball_reduced_against_oracle_and_full_size_properties(gpu):
-    """hairball: oracle parity on a reduced mesh; the full 2.88 M-triangle mesh at 1920x1080x8spp must
-    trace exactly W*H*spp primary rays, one shadow ray per hit, and be reproducible."""
-    scene, camd, cfg = configs.build("C4", target_tris=320000)
-    w, h = 384, 216
+def test_c4_full_mesh_against_oracle_and_full_size_properties(gpu):
+    """hairball: the FULL 2.88 M-triangle mesh against the f64 oracle at a reduced resolution (480x270, 2 spp — the oracle
+    needs ~100 node visits per ray here); at 1920x1080x8spp it must trace exactly W*H*spp primary rays, one shadow ray per
+    hit, and be reproducible."""
+    scene, camd, cfg = configs.build("C4")
+    w, h = 480, 270
     cam = make_camera(w, h, 2, 1.0, camd.eye, camd.projection((w, h)), seed=0)
     img, st = render_np(gpu, scene, cam)
     ref, ost = O.OracleScene(scene.flat, 64).render(cam)
-    m = image_metrics(img, ref)
-    assert m["frac_over"] <= 2e-3, m
+    # hair strands are thinner than a pixel: almost every pixel touches a silhouette, so flips are common and legitimate
+    rec = assert_parity(img, ref, what="C4 full mesh 480x270x2", wh=(w, h), max_frac=MAX_FRAC_OVER)
+    assert rec["mean_abs"] < 5e-4, rec
     assert abs(int(st.rays_shadow) - int(ost.rays_shadow)) <= 2e-3 * ost.rays_shadow + 4
-    scene.close()
-    scene, camd, cfg = configs.build("C4")
     w, h, spp = cfg["width"], cfg["height"], cfg["spp"]
     cam = make_camera(w, h, spp, cfg["window"], camd.eye, camd.projection((w, h)), seed=0)
     a, sa = render_np(gpu, scene, cam)
@@ -120,4 +152,11 @@ def test_c4_hairball_reduced_against_oracle_and_full_size_properties(gpu):
     assert sa.rays_reflect == 0 and sa.rays_refract == 0
     assert 0 < sa.rays_shadow < sa.rays_primary          # misses see the background and cast no shadow ray
     assert np.abs(a - b).max() < 1e-5
+    # a full-size band against the oracle too (8 rows through the middle of the ball, all 8 spp)
+    osc = O.OracleScene(scene.flat, 64)
+    ref = np.zeros_like(a)
+    y0 = 536
+    osc.render(cam, 0, y0 * w, 8 * w, ref)
+    rows = slice(y0 * w, (y0 + 8) * w)
+    assert_parity(a[rows], ref[rows], what="C4 full size band 1920x8x8spp", wh=(w, 8), max_frac=MAX_FRAC_OVER)
     scene.close()

@@ -33,7 +33,7 @@ def test_f32_twin_close_to_golden(name):
     scene, _camd, cam, _ = G.build_case(name)
     img, _ = O.OracleScene(scene.flat, 32).render(cam)
     gold, _ = load(name)
-    assert_parity(img, gold, max_frac=3e-3, what=name)
+    assert_parity(img, gold, what="f32twin/" + name, wh=(cam.width, cam.height))
 
 
 @pytest.mark.gpu
@@ -49,7 +49,7 @@ def test_device_matches_golden(gpu, name):
     st = A.NrbStats()
     _lib.check(gpu.nrb_render(scene.handle, C.byref(cam), out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(st)))
     gold, counts = load(name)
-    m = assert_parity(out, gold, max_frac=3e-3, what=name)
+    m = assert_parity(out, gold, what="golden/" + name, wh=(w, h))
     assert m["mean_abs"] < 1e-3   # a few silhouette flips on a ~5 k-pixel image dominate the mean
     got = [st.rays_primary, st.rays_reflect, st.rays_refract, st.rays_shadow, st.paths_truncated]
     assert got[0] == counts[0]

@@ -52,7 +52,7 @@ def test_shape_zoo_phong(gpu):
     mats = [phong(tex=tex), phong(tex=tex), phong(), phong(kd=(0.2, 0.9, 0.3)), phong(ks=(0, 0, 0))]
     lights = [Light((2, 4, -3), 0.0, 1, (1.0, 0.9, 0.8)), Light((-3, 2, -2), 0.0, 1, (0.3, 0.3, 0.5))]
     img, st, ref, ost = render_both(zoo(mats), lights, eye=(0.5, 2.0, -7.0), w=160, h=96)
-    assert_parity(img, ref, what="zoo/phong")
+    assert_parity(img, ref, what="zoo/phong", wh=(160, 96))
     assert_counts_close(st, ost)
 
 
@@ -62,7 +62,7 @@ def test_shape_zoo_debug_materials_and_texture_modes(gpu):
     mats = [UVMaterial(), NormalMaterial(), UVMaterial(), NormalMaterial(), phong(tex=t1)]
     nodes = zoo(mats) + [node(Cuboid((0.4, 0.4, 0.4)), phong(tex=t2), pos=(0, 1.5, 1.0), angle=(45, 0, 30))]
     img, st, ref, ost = render_both(nodes, [Light((0, 5, -4), 0.0, 1, (1, 1, 1))], eye=(0.0, 1.5, -7.5), w=160, h=96)
-    assert_parity(img, ref, what="zoo/debug")
+    assert_parity(img, ref, what="zoo/debug", wh=(160, 96))
     assert_counts_close(st, ost)
 
 
@@ -75,7 +75,7 @@ def test_transparency_refraction_reflection_chain(gpu):
         nodes.append(node(g, m, pos=(-3.2 + 1.6 * i, 0.0, 0.0), angle=(0, 15 * i, 0), alpha=0.3 + 0.1 * i, refr=1.3))
     nodes.append(node(Plane((0, 1, 0)), phong(), pos=(0, -1.2, 0), refl=(0.3, 0.4)))
     img, st, ref, ost = render_both(nodes, [Light((0, 5, -2), 0.0, 1, (1, 1, 1))], eye=(0.0, 2.0, -7.0), w=160, h=96)
-    assert_parity(img, ref, what="glass")
+    assert_parity(img, ref, what="glass", wh=(160, 96))
     assert_counts_close(st, ost)
     assert st.rays_refract > 0 and st.rays_reflect > 0
 
@@ -85,7 +85,7 @@ def test_area_light_and_jitter_share_the_rng(gpu):
     nodes = [node(Ball(1.0), phong(), pos=(0, 0, 0)), node(Plane((0, 1, 0)), phong(), pos=(0, -1, 0))]
     lights = [Light((1.5, 3, -1), 0.6, 10, (1, 1, 1))]  # 9 samples
     img, st, ref, ost = render_both(nodes, lights, eye=(0, 1.5, -5), w=96, h=64, spp=3, window=1.0, seed=11)
-    assert_parity(img, ref, max_frac=2e-3, what="area light")
+    assert_parity(img, ref, what="area light", wh=(96, 64))
     assert st.rays_shadow == ost.rays_shadow or abs(int(st.rays_shadow) - int(ost.rays_shadow)) < 0.002 * ost.rays_shadow
     img2, _, _, _ = render_both(nodes, lights, eye=(0, 1.5, -5), w=96, h=64, spp=3, window=1.0, seed=12)
     assert np.abs(img2 - img).max() > 1e-3  # a different seed gives a different frame
@@ -105,7 +105,7 @@ def test_alpha_mapped_mesh_and_per_node_shadow_semantics(gpu):
     nodes = [node(two_layers, phong(ka=(0.3, 0.3, 0.3), amap=amap)), node(TriMesh(Pf, Ff, UVf), phong()),
              node(TriMesh(P + np.float32([0, 1.2, 0]), F, UV), phong(ka=(0.5, 0.2, 0.2)), alpha=0.4)]
     img, st, ref, ost = render_both(nodes, [Light((0.5, 6, -0.5), 0.0, 1, (1, 1, 1))], eye=(0.0, 3.0, -6.0), w=160, h=120)
-    assert_parity(img, ref, max_frac=2e-3, what="alpha map")
+    assert_parity(img, ref, what="alpha map", wh=(160, 120))
     assert_counts_close(st, ost)   # rays_shadow counts the reference's light samples, cast or not
     # hits on fully transparent texels carry weight 0: their light samples add exactly nothing and are not cast
     assert 0 < st.rays_shadow_culled < st.rays_shadow and ost.rays_shadow_culled == 0
@@ -138,7 +138,7 @@ def test_nmap_depth_shift_nodes(gpu):
              node(Plane((0, 1, 0)), phong(), pos=(0, -1.2, 0), refl=(0.3, 0.5))]
     lights = [Light((1.5, 5.0, -3.0), 0.0, 1, (1, 1, 1)), Light((-3.0, 4.0, -2.0), 0.3, 4, (0.6, 0.6, 0.9))]
     img, st, ref, ost = render_both(nodes, lights, eye=(0.3, 1.6, -6.5), w=160, h=112, spp=2, window=1.0, seed=3)
-    assert_parity(img, ref, max_frac=3e-3, what="nmap")
+    assert_parity(img, ref, what="nmap", wh=(160, 112))
     assert_counts_close(st, ost)
     # and the shift is really in the picture: the same scene without the textures differs
     plain = [SceneNode(n.material, n.refl_mix, n.refl_atenuation, n.alpha, n.refr_coeff, n.transform, n.geometry, None, n.solid) for n in nodes]
@@ -156,20 +156,20 @@ def test_solid_flag_and_camera_inside_objects(gpu):
     nodes = [node(Ball(3.0), phong(), pos=(0, 0, 0), solid=False), node(Cuboid((0.5, 0.5, 0.5)), NormalMaterial(), pos=(0, 0, 1.5)),
              node(Cylinder(0.4, 0.3), UVMaterial(), pos=(1.2, 0, 1.0))]
     img, st, ref, ost = render_both(nodes, [Light((0, 1, 0), 0.0, 1, (1, 1, 1))], eye=(0, 0, -1.0), at=(0, 0, 1), w=96, h=64)
-    assert_parity(img, ref, what="inside ball")
+    assert_parity(img, ref, what="inside ball", wh=(96, 64))
     nodes[0] = node(Ball(3.0), phong(), pos=(0, 0, 0), solid=True)   # toi 0 everywhere
     img, st, ref, ost = render_both(nodes, [Light((0, 1, 0), 0.0, 1, (1, 1, 1))], eye=(0, 0, -1.0), at=(0, 0, 1), w=96, h=64)
-    assert_parity(img, ref, max_frac=5e-3, what="solid ball")
+    assert_parity(img, ref, what="solid ball", wh=(96, 64))
 
 
 def test_transparent_plane_candidate_and_plane_only_scene(gpu):
     nodes = [node(Plane((0, 0, -1)), phong(ka=(0.2, 0.3, 0.4)), pos=(0, 0, 2), alpha=0.5),
              node(Plane((0, 1, 0)), phong(), pos=(0, -1, 0)), node(Ball(0.7), phong(), pos=(0.3, 0, 4))]
     img, st, ref, ost = render_both(nodes, [Light((0, 3, -3), 0.0, 1, (1, 1, 1))], eye=(0, 1, -4), w=96, h=64)
-    assert_parity(img, ref, what="transparent plane")
+    assert_parity(img, ref, what="transparent plane", wh=(96, 64))
     assert_counts_close(st, ost)
     img, st, ref, ost = render_both(nodes[:2], [Light((0, 3, -3), 0.0, 1, (1, 1, 1))], eye=(0, 1, -4), w=64, h=48)
-    assert_parity(img, ref, what="planes only")
+    assert_parity(img, ref, what="planes only", wh=(64, 48))
 
 
 def test_depth_cap_matches_oracle(gpu):
@@ -177,7 +177,7 @@ def test_depth_cap_matches_oracle(gpu):
            node(Plane((0, -1, 0)), NormalMaterial(), pos=(0, 1, 0), refl=(0.6, 0.0)),
            node(Plane((0, 0, -1)), UVMaterial(), pos=(0, 0, 6))]
     img, st, ref, ost = render_both(mir, [], eye=(0, 0.2, -3), at=(0, 0.1, 0), w=64, h=48, max_depth=9)
-    assert_parity(img, ref, what="mirror box")
+    assert_parity(img, ref, what="mirror box", wh=(64, 48))
     assert st.paths_truncated == ost.paths_truncated > 0
     assert st.rays_reflect == ost.rays_reflect
 
@@ -199,8 +199,7 @@ def test_ragged_resolutions(gpu, w, h, spp):
     nodes = [node(Ball(1.0), phong(), pos=(0, 0, 0)), node(Plane((0, 1, 0)), NormalMaterial(), pos=(0, -1, 0))]
     img, st, ref, ost = render_both(nodes, [Light((2, 3, -2), 0.0, 1, (1, 1, 1))], eye=(0, 1, -4), w=w, h=h, spp=spp, window=1.0, seed=4)
     assert st.rays_primary == w * h * spp
-    m = image_metrics(img, ref)
-    assert m["frac_over"] <= max(2.0 / (w * h), 2e-3), m
+    assert_parity(img, ref, what="ragged %dx%dx%d" % (w, h, spp), wh=(w, h))
 
 
 def test_error_codes(gpu):
@@ -394,7 +393,7 @@ def _glass_mirror_scene():
 def test_both_children_spill_and_area_light(gpu):
     nodes, lights = _glass_mirror_scene()
     img, st, ref, ost = render_both(nodes, lights, eye=(0, 1.5, -5.5), w=128, h=96, spp=2, window=1.0, seed=3)
-    assert_parity(img, ref, max_frac=2e-3, what="both children")
+    assert_parity(img, ref, what="both children", wh=(128, 96))
     assert_counts_close(st, ost)
     assert st.rays_reflect > 0 and st.rays_refract > 0
 
@@ -413,7 +412,7 @@ def test_driver_paths_give_the_same_image(gpu, env):
         img, st, _, _ = render_both(nodes, lights, eye=(0, 1.5, -5.5), w=96, h=80, spp=2, window=1.0, seed=8)
     np.testing.assert_allclose(img, base, rtol=0, atol=3e-5)   # only the order of float atomics may differ
     assert st.as_dict()["rays_total"] == st0.as_dict()["rays_total"]
-    assert_parity(img, ref, max_frac=2e-3, what=str(env))
+    assert_parity(img, ref, what=str(env), wh=(96, 80))
 
 
 def test_mesh_scene_driver_paths(gpu):
