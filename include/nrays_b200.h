@@ -38,7 +38,8 @@ enum {
   NRB_ERR_CUDA = 2,           /* any CUDA runtime failure (message has the CUDA string) */
   NRB_ERR_NO_DEVICE = 3,      /* no sm_100 device visible: the product path never falls back to CPU */
   NRB_ERR_QUEUE_OVERFLOW = 4, /* ray queues would exceed the configured memory ceiling */
-  NRB_ERR_UNSUPPORTED = 5     /* feature outside the flattened format (e.g. user-defined Material impl) */
+  NRB_ERR_UNSUPPORTED = 5,    /* feature outside the flattened format (e.g. user-defined Material impl) */
+  NRB_ERR_INTERNAL = 6        /* a self-check of the library failed (BVH invariant): a bug in this library, not in the input */
 };
 
 /* ---- shape kinds: ncollide3d shapes built at examples/loader3d.rs:593-659,695 */
@@ -167,8 +168,8 @@ typedef struct NrbStats {
   uint32_t waves;           /* wavefront iterations */
   uint32_t kernel_launches; /* this library's kernels launched by the call */
   float ms_device;          /* CUDA-event span raygen -> resolve on the render stream */
-  float ms_trace;           /* CUDA-event time of the trace kernel launches (closest hit + shadow rays) */
-  float ms_shade;           /* ms_device - ms_trace: shade + resolve + inter-kernel gaps */
+  float ms_trace;           /* CUDA-event time of the trace_kernel launches ONLY (closest hit + shadow rays; not the tail kernel) */
+  float ms_shade;           /* ms_device - ms_trace - ms_tail: shade + resolve + inter-kernel gaps */
   uint32_t _pad;
   uint64_t bvh_nodes;       /* device BVH size, for the roofline's scene_bytes */
   uint64_t triangles;
@@ -177,6 +178,12 @@ typedef struct NrbStats {
   uint32_t launches_shade;  /* launches of the shade kernel */
   uint64_t rays_shadow_culled; /* of rays_shadow: light samples whose contribution is exactly zero (weight 0, e.g. hits on
                                 * fully transparent texels) — the reference casts them, this library does not */
+  float ms_tail;            /* CUDA-event time of the tail kernel launches (ray chains followed per lane) */
+  float ms_shade_kernel;    /* CUDA-event time of the shade_kernel launches alone */
+  uint32_t launches_tail;   /* launches of the tail kernel */
+  uint32_t _pad2;
+  uint64_t rays_tail;       /* closest-hit queries answered inside the tail kernel (the rest went through trace_kernel);
+                             * every shadow query goes through trace_kernel */
 } NrbStats;
 
 typedef struct NrbScene NrbScene; /* opaque handle == Arc<Scene> of the reference */
@@ -214,7 +221,8 @@ typedef struct NrbBuildOptions {
   uint32_t _reserved[3];
 } NrbBuildOptions;
 
-/* nrb_scene_create with options (NULL = defaults).  Env NRB_BUILDER=sah|lbvh overrides, for experiments. */
+/* nrb_scene_create with options.  opts == NULL: defaults, and only then the environment variable NRB_BUILDER=sah|lbvh
+ * is consulted (experiments); an explicit NrbBuildOptions always wins. */
 int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOptions *opts, NrbScene **out);
 
 /* How the scene behind a handle was built. */

@@ -14,6 +14,7 @@ NRB_ERR_CUDA = 2
 NRB_ERR_NO_DEVICE = 3
 NRB_ERR_QUEUE_OVERFLOW = 4
 NRB_ERR_UNSUPPORTED = 5
+NRB_ERR_INTERNAL = 6
 
 NRB_SHAPE_BALL = 0
 NRB_SHAPE_CUBOID = 1
@@ -144,6 +145,11 @@ class NrbStats(C.Structure):
         ("launches_trace", C.c_uint32),
         ("launches_shade", C.c_uint32),
         ("rays_shadow_culled", C.c_uint64),
+        ("ms_tail", C.c_float),
+        ("ms_shade_kernel", C.c_float),
+        ("launches_tail", C.c_uint32),
+        ("_pad2", C.c_uint32),
+        ("rays_tail", C.c_uint64),
     ]
 
     @property

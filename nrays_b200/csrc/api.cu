@@ -85,6 +85,7 @@ struct NrbScene {
   bool has_shapes = false;
   bool has_nmap = false;  // some node carries a depth-shift texture: general trace kernel (kernels.cu: trace_general_kernel)
   int child_factor = 0;  // max secondary rays per ray (reflection + refraction possible in this scene)
+  uint32_t refl_chain_max = 0;  // most reflections one ray chain can make before its energy is spent (0xFFFFFFFF: unbounded)
   uint64_t n_bvh_nodes = 0, n_tris = 0, scene_bytes = 0;
   int grid_trace = 148, grid_tail = 148;
   NrbBuildInfo build_info{};
@@ -181,6 +182,7 @@ struct HostScene {
   int root_all = kEmpty, root_opaque = kEmpty;
   int shadow_samples = 0;
   bool any_refl = false, any_refr = false;
+  uint32_t refl_chain_max = 0;
   int depth_tri = 0, depth_mid = 0, depth_top = 0;
   float gpu_build_ms = 0.0f;  // device time of the LBVH kernels (NRB_BUILDER_LBVH)
 };
@@ -261,6 +263,13 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
     is_cand[i] = cand ? 1 : 0;
     any_refl = any_refl || (n.refl_mix != 0.0f);
     any_refr = any_refr || may_refract;
+    if (n.refl_mix != 0.0f) {
+      // trace_reflection reflects while energy > 0.1 and pays refl_atenuation per bounce (src/scene.rs:204-208): a chain
+      // that only meets this node reflects at most ceil(0.9 / att) times (+1 for f32 rounding of the energy sequence)
+      const float att = n.refl_atenuation;
+      const uint32_t r = (att > 0.0f && 0.9f / att < 1.0e6f) ? (uint32_t)std::ceil(0.9f / att) + 1u : 0xFFFFFFFFu;
+      H.refl_chain_max = std::max(H.refl_chain_max, r);
+    }
     NodeInfo ni{};
     ni.material = n.material;
     ni.refl_mix = n.refl_mix;
@@ -686,6 +695,7 @@ int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
   S.has_nmap = !H.nmaps.empty();
   S.has_shapes = !H.shapes.empty() || S.has_nmap;  // the general (HAS_SHAPES) kernel variants carry the nmap code
   S.child_factor = (H.any_refl ? 1 : 0) + (H.any_refr ? 1 : 0);
+  S.refl_chain_max = H.refl_chain_max;
   S.n_bvh_nodes = H.nodes.size();
   S.n_tris = H.tris.size();
   S.scene_bytes = H.nodes.size() * sizeof(BvhNode) + H.tris.size() * (sizeof(Tri) + sizeof(TriUV)) +
@@ -701,6 +711,9 @@ int make_frame_params(const NrbCamera &cam, const NrbTileSet *tiles, FrameParams
   if (cam.width == 0 || cam.height == 0) return fail(NRB_ERR_INVALID_ARG, "resolution must be non-zero");
   uint64_t samples = (uint64_t)cam.width * cam.height * cam.ray_per_pixel;
   if (samples >= (1ull << 32)) return fail(NRB_ERR_INVALID_ARG, "width*height*ray_per_pixel must be < 2^32");
+  // sample slots count PADDED 16x16 tiles (ragged frames have more slots than samples) and are 32-bit on the device
+  if ((uint64_t)((cam.width + NRB_TILE - 1) / NRB_TILE) * ((cam.height + NRB_TILE - 1) / NRB_TILE) * (NRB_TILE * NRB_TILE) * cam.ray_per_pixel >= (1ull << 32))
+    return fail(NRB_ERR_INVALID_ARG, "tiles_x*tiles_y*256*ray_per_pixel must be < 2^32");
   std::memset(&fp, 0, sizeof(fp));
   fp.width = cam.width, fp.height = cam.height, fp.spp = cam.ray_per_pixel;
   fp.max_depth = cam.max_depth ? cam.max_depth : 64u;
@@ -792,7 +805,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   uint32_t launches = 0, waves = 0;
   size_t wave_counts_used = 0;
   size_t ev_used = 0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_spans, shade_spans;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_spans, shade_spans, tail_spans;
   const bool dump = getenv("NRB_DUMP_WAVES") != nullptr;
 
   {
@@ -888,7 +901,15 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
         }
         if (known_prev == 0 || S.child_factor == 0) break;
         bound = known_prev * (uint64_t)S.child_factor;
-        if (k >= tail_min_wave && bound <= tail_threshold) {
+        // Tail launches spill the refraction ray of every hit that wants BOTH children while the lane follows the reflection.
+        // A chain reflects at most min(levels left, refl_chain_max) times, which bounds the spill queue exactly; scenes where
+        // that bound is too large for a queue (mirror-glass with tiny attenuation) stay on the wave path, whose queues are
+        // sized per wave and cannot overflow.
+        const uint64_t spill_limit = env_size("NRB_SPILL_CAP", 64u << 20);
+        auto spill_factor = [&](uint32_t level) -> uint64_t {
+          return S.child_factor < 2 ? 0ull : std::min<uint64_t>(fp.max_depth - level, S.refl_chain_max);
+        };
+        if (k >= tail_min_wave && bound <= tail_threshold && bound * spill_factor(k) <= spill_limit) {
           // (every ray of the tail phase descends from a ray of wave k-1, so at most known_prev pixels can still change;
           //  with more than that the patch would rival the image itself)
           if (early_h_out && early_used && !*early_used && fp.n_local_tiles <= tiles_per_batch && d_out && !fp.packed &&
@@ -908,7 +929,8 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
           for (uint32_t t = k; t < fp.max_depth; ++t) {
             const int tc = (int)(t & 1u);
             if (wave_base + t + 1 >= S.h_wave_cap) return fail(NRB_ERR_INVALID_ARG, "max_depth too large for the wave-count buffer");
-            CU(ensure_ray_queue(S, 1 - tc, (uint32_t)std::max<uint64_t>(bound * 4, 4096)));  // spill queue
+            if (bound * spill_factor(t) >= (1ull << 32)) return fail(NRB_ERR_QUEUE_OVERFLOW, "tail spill queue would exceed 2^32 entries");
+            CU(ensure_ray_queue(S, 1 - tc, (uint32_t)std::max<uint64_t>(bound * spill_factor(t), 1024)));  // spill queue, exact bound
             if (S_total && S.sq_cap < 65536) {
               if (pending_shadow >= 0) {  // the buffer is about to move: trace what it holds first
                 rc = trace_span(false, no_queue, nullptr, &wc[pending_shadow]);
@@ -926,7 +948,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
             launch_tail(S.view, S.has_shapes, fp, ray_queue(S, tc), &wc[t], ray_queue(S, 1 - tc), sq, dc, accum, &wc[sh_wave],
                         S.grid_tail, st);
             CU(cudaEventRecord(e1, st));
-            trace_spans.emplace_back(e0, e1);
+            tail_spans.emplace_back(e0, e1);
             ++launches;
             if (S_total) {
               rc = trace_span(false, no_queue, nullptr, &wc[sh_wave]);  // pending shadow rays + the chains' shadow rays
@@ -1003,25 +1025,24 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
       if (rc) return rc;
       pending_shadow = -1;
       if (!chunked) {
-        cudaEvent_t h0 = nullptr, h1 = nullptr;
-        if (dump) {
-          h0 = get_event(S, ev_used), h1 = get_event(S, ev_used);
-          CU(cudaEventRecord(h0, st));
-        }
+        cudaEvent_t h0 = get_event(S, ev_used), h1 = get_event(S, ev_used);
+        CU(cudaEventRecord(h0, st));
         launch_shade(S.view, S.has_shapes, fp, k == 0, qin, S.d_hits.as<float4>(), &wc[k], slot_lo, n_slots, 0, n_upper,
                      ray_queue(S, 1 - cur), sq, dc, accum, S.grid_shade, st);
-        if (dump) {
-          CU(cudaEventRecord(h1, st));
-          shade_spans.emplace_back(h0, h1);
-        }
+        CU(cudaEventRecord(h1, st));
+        shade_spans.emplace_back(h0, h1);
         ++launches;
         if (S_total) pending_shadow = (int)k;
       } else {
         // rare path (area lights x huge waves): shade a slice, trace its shadow rays, repeat
         for (uint32_t lo = 0; lo < n_upper; lo += chunk) {
           uint32_t hi = (uint32_t)std::min<uint64_t>(n_upper, (uint64_t)lo + chunk);
+          cudaEvent_t h0 = get_event(S, ev_used), h1 = get_event(S, ev_used);
+          CU(cudaEventRecord(h0, st));
           launch_shade(S.view, S.has_shapes, fp, k == 0, qin, S.d_hits.as<float4>(), &wc[k], slot_lo, n_slots, lo, hi,
                        ray_queue(S, 1 - cur), sq, dc, accum, S.grid_shade, st);
+          CU(cudaEventRecord(h1, st));
+          shade_spans.emplace_back(h0, h1);
           ++launches;
           rc = trace_span(false, no_queue, nullptr, &wc[k]);
           if (rc) return rc;
@@ -1095,10 +1116,23 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
       cudaEventElapsedTime(&t, sp.first, sp.second);
       tt += t;
     }
+    auto span_ms = [](const std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &v) {
+      float sum = 0.0f;
+      for (auto &sp : v) {
+        float t = 0.0f;
+        cudaEventElapsedTime(&t, sp.first, sp.second);
+        sum += t;
+      }
+      return sum;
+    };
     stats->ms_trace = tt;
-    stats->ms_shade = ms - tt;
+    stats->ms_tail = span_ms(tail_spans);
+    stats->ms_shade_kernel = span_ms(shade_spans);
+    stats->ms_shade = ms - tt - stats->ms_tail;
     stats->launches_trace = (uint32_t)trace_spans.size();
-    stats->launches_shade = launches - 1u - (uint32_t)trace_spans.size();
+    stats->launches_tail = (uint32_t)tail_spans.size();
+    stats->launches_shade = (uint32_t)shade_spans.size();
+    stats->rays_tail = S.h_counters->rays_tail;
     stats->bvh_nodes = S.n_bvh_nodes;
     stats->triangles = S.n_tris;
     stats->scene_bytes = S.scene_bytes;
@@ -1133,7 +1167,9 @@ int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out) {
 int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOptions *opts, NrbScene **out) {
   if (!desc || !out) return fail(NRB_ERR_INVALID_ARG, "desc/out is NULL");
   uint32_t builder = opts ? opts->builder : NRB_BUILDER_SAH;
-  if (const char *e = getenv("NRB_BUILDER")) builder = (std::string(e) == "lbvh") ? NRB_BUILDER_LBVH : NRB_BUILDER_SAH;
+  if (!opts) {  // the environment only fills in for a caller that expressed no choice
+    if (const char *e = getenv("NRB_BUILDER")) builder = (std::string(e) == "lbvh") ? NRB_BUILDER_LBVH : NRB_BUILDER_SAH;
+  }
   if (builder != NRB_BUILDER_SAH && builder != NRB_BUILDER_LBVH) return fail(NRB_ERR_INVALID_ARG, "unknown builder");
   if (desc->struct_size != sizeof(NrbSceneDesc) || desc->abi_version != NRB_ABI_VERSION)
     return fail(NRB_ERR_INVALID_ARG, "NrbSceneDesc struct_size / abi_version mismatch");
@@ -1159,7 +1195,7 @@ int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOp
   if (rc) return rc;
   if (getenv("NRB_CHECK_BVH")) {  // structural self-check of whatever builder ran (tests)
     std::string why;
-    if (check_bvh(H, why) || check_device_nodes(H, why)) return fail(NRB_ERR_CUDA + 100, "internal BVH invariant violated: " + why);
+    if (check_bvh(H, why) || check_device_nodes(H, why)) return fail(NRB_ERR_INTERNAL, "internal BVH invariant violated: " + why);
   }
   rc = upload_scene(*desc, H, *S);
   if (rc) return rc;
@@ -1197,7 +1233,7 @@ int nrb_scene_validate(const NrbSceneDesc *desc, NrbBuildInfo *info) {
   if (rc) return rc;
   double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   std::string why;
-  if (check_bvh(H, why) || check_device_nodes(H, why)) return fail(NRB_ERR_CUDA + 100, "internal BVH invariant violated: " + why);
+  if (check_bvh(H, why) || check_device_nodes(H, why)) return fail(NRB_ERR_INTERNAL, "internal BVH invariant violated: " + why);
   if (const char *path = getenv("NRB_DUMP_BVH")) {  // builder experiments (scripts/bvh_sim.cpp): nodes + triangles as built
     if (FILE *f = fopen(path, "wb")) {
       uint64_t hdr[4] = {H.nodes.size(), H.tris.size(), (uint64_t)(uint32_t)H.root_all, (uint64_t)(uint32_t)H.root_opaque};

@@ -163,6 +163,7 @@ struct Counters {
   uint32_t _pad[3];
   unsigned long long rays_reflect, rays_refract, rays_shadow, paths_truncated;
   unsigned long long rays_shadow_culled;  // light samples not cast because their contribution is exactly zero
+  unsigned long long rays_tail;           // closest-hit queries answered inside the tail kernel
   unsigned long long dbg_nodes, dbg_tris, dbg_rays;  // -DNRB_COUNT_VISITS builds only
 };
 

@@ -990,7 +990,9 @@ NRB_DI void light_sample(const SceneView &sc, const FrameParams &fp, const RaySt
   V3 pos = mk(L.pos[0], L.pos[1], L.pos[2]);
   if (L.radius != 0.0f) {
     uint32_t rnd[4];
-    philox4x32_10(s.ipt, s.smp, r.path, ((uint32_t)li << 16) | (k & 0xFFFFu), fp.seed_lo, fp.seed_hi ^ kStreamLight, rnd);
+    // r.path doubles per bounce and wraps after 32 of them: the key takes depth / 32 so deeper paths keep their own streams
+    philox4x32_10(s.ipt, s.smp, r.path, ((uint32_t)li << 16) | (k & 0xFFFFu), fp.seed_lo,
+                  fp.seed_hi ^ kStreamLight ^ ((r.depth >> 5) * 0x9E3779B9u), rnd);
     pos = pos + mk(u24(rnd[0]), u24(rnd[1]), u24(rnd[2])) * L.radius;
   }
   ldir = pos - s.pt;
@@ -1197,7 +1199,7 @@ __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : kTailMinBlocks) 
   const uint32_t lane = lane_id();
   const uint32_t count = wc[0].n_rays;
   const uint32_t S = (uint32_t)sc.shadow_samples;
-  uint32_t c_shadow = 0, c_refl = 0, c_refr = 0, c_trunc = 0, c_culled = 0;
+  uint32_t c_shadow = 0, c_refl = 0, c_refr = 0, c_trunc = 0, c_culled = 0, c_tail = 0;
   while (true) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(&wc[0].fetch_closest, 32u);
@@ -1208,6 +1210,7 @@ __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : kTailMinBlocks) 
       RayState r = load_ray(qin, i);
       while (true) {
         float4 h = closest_hit<HAS_SHAPES>(sc, r.o, r.d);
+        ++c_tail;
         Shaded s;
         shade_eval<HAS_SHAPES>(sc, fp, r, h, true, accum, s);
         c_trunc += (s.trunc_refl ? 1u : 0u) + (s.trunc_refr ? 1u : 0u);
@@ -1242,6 +1245,8 @@ __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : kTailMinBlocks) 
     }
   }
   flush_stats(ctr, c_shadow, c_refl, c_refr, c_trunc, c_culled);
+  c_tail = __reduce_add_sync(0xFFFFFFFFu, c_tail);
+  if (lane == 0 && c_tail) atomicAdd(&ctr->rays_tail, (unsigned long long)c_tail);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -133,11 +133,15 @@ class PeerImage:
         self.lib, self.rank, self.world, self.device, self.owner = _lib.load(), rank, world, int(device), owner
         self.n_floats = width * height * 3
         self.ptr = C.c_void_p()
+        # NCCL: collectives on CUDA tensors, ordered on the render stream.  Any other backend (gloo in the tests): the
+        # stream is drained first and the collective runs on host tensors — same ordering, paid with a host sync.
+        self._on_device = td.get_backend() == "nccl"
+        self._cdev = ("cuda:%d" % self.device) if self._on_device else "cpu"
         handle = A.NrbIpcHandle()
         ok = True
         if rank == owner:
             ok = self.lib.nrb_ipc_alloc(self.device, self.n_floats * 4, C.byref(self.ptr), C.byref(handle)) == A.NRB_OK
-        hb = torch.tensor(list(bytes(handle.bytes)) + [1 if ok else 0], dtype=torch.uint8, device="cuda:%d" % self.device)
+        hb = torch.tensor(list(bytes(handle.bytes)) + [1 if ok else 0], dtype=torch.uint8, device=self._cdev)
         td.broadcast(hb, src=owner)
         raw = hb.cpu().numpy().tobytes()
         if not raw[64]:
@@ -146,9 +150,9 @@ class PeerImage:
             C.memmove(handle.bytes, raw[:64], 64)
             ok = self.lib.nrb_ipc_open(self.device, C.byref(handle), C.byref(self.ptr)) == A.NRB_OK
         # every rank must know whether every rank has the mapping
-        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda:%d" % self.device)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self._cdev)
         td.all_reduce(flag, op=td.ReduceOp.MIN)
-        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.device)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self._cdev)
         if int(flag.item()) == 0:
             self.close()
             raise RuntimeError("PeerImage: CUDA IPC mapping failed on some rank: " + self.lib.nrb_last_error().decode("utf-8", "replace"))
@@ -160,11 +164,23 @@ class PeerImage:
         assert self.rank == self.owner
         return torch.as_tensor(_DevArray(self.ptr.value, self.n_floats), device="cuda:%d" % self.device)
 
-    def sync(self):
-        """Orders all ranks' peer stores before whatever the owner enqueues next on its current stream."""
+    def _fence(self):
+        import torch
         import torch.distributed as td
 
+        if not self._on_device:
+            torch.cuda.synchronize(self.device)
         td.all_reduce(self._flag)
+
+    def sync(self):
+        """WRITERS -> READER: orders all ranks' peer stores before whatever the owner enqueues next on its current stream."""
+        self._fence()
+
+    def release(self):
+        """READER -> WRITERS: call on every rank after the owner has enqueued its reads of this frame (copy to the host,
+        encode, ...).  The next frame's peer stores of every rank are ordered behind those reads; without it rank r may
+        be storing frame i+1 into the image while the owner still copies frame i (write-after-read race)."""
+        self._fence()
 
     def close(self):
         if self.ptr:
@@ -205,14 +221,19 @@ class SharedHostImage:
         self.lib, self.rank, self.world, self.device = _lib.load(), rank, world, int(device)
         self.nbytes = width * height * 3 * 4
         self.shm, self.array, self._cbuf, self._registered, self.addr = None, None, None, False, 0
+        self._on_device = td.get_backend() == "nccl"
+        cdev = ("cuda:%d" % self.device) if self._on_device else "cpu"
         name = [None]
         if rank == 0:
-            self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
-            name[0] = self.shm.name
+            try:  # a failure here (e.g. /dev/shm full) must still reach the broadcast, or the other ranks wait forever
+                self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
+                name[0] = self.shm.name
+            except Exception:
+                name[0] = None
         td.broadcast_object_list(name, src=0)
-        ok = True
+        ok = name[0] is not None
         try:
-            if rank != 0:
+            if ok and rank != 0:
                 self.shm = shared_memory.SharedMemory(name=name[0])
                 try:  # only the owner unlinks the segment; keep this process's resource tracker out of it
                     from multiprocessing import resource_tracker
@@ -220,25 +241,29 @@ class SharedHostImage:
                     resource_tracker.unregister(self.shm._name, "shared_memory")
                 except Exception:
                     pass
-            self.array = np.ndarray((width * height * 3,), dtype=np.float32, buffer=self.shm.buf)
-            self._cbuf = C.c_char.from_buffer(self.shm.buf)
-            self.addr = C.addressof(self._cbuf)
-            dptr = C.c_void_p()
-            ok = self.lib.nrb_host_register(self.device, C.c_void_p(self.addr), self.nbytes, C.byref(dptr)) == A.NRB_OK
-            self._registered = ok
+            if ok:
+                self.array = np.ndarray((width * height * 3,), dtype=np.float32, buffer=self.shm.buf)
+                self._cbuf = C.c_char.from_buffer(self.shm.buf)
+                self.addr = C.addressof(self._cbuf)
+                dptr = C.c_void_p()
+                ok = self.lib.nrb_host_register(self.device, C.c_void_p(self.addr), self.nbytes, C.byref(dptr)) == A.NRB_OK
+                self._registered = ok
         except Exception:
             ok = False
-        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda:%d" % self.device)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=cdev)
         td.all_reduce(flag, op=td.ReduceOp.MIN)
-        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.device)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=cdev)
         if int(flag.item()) == 0:
             self.close()
             raise RuntimeError("SharedHostImage: shared memory / cudaHostRegister failed on some rank")
 
     def sync(self):
         """All ranks' DMAs have landed when this all-reduce completes (each rank's render call returns after its own)."""
+        import torch
         import torch.distributed as td
 
+        if not self._on_device:
+            torch.cuda.synchronize(self.device)
         td.all_reduce(self._flag)
 
     def close(self):
@@ -249,11 +274,14 @@ class SharedHostImage:
         self._cbuf = None
         if self.shm is not None:
             try:
-                self.shm.close()
-                if self.rank == 0:
-                    self.shm.unlink()
+                self.shm.close()  # raises BufferError while a caller still holds a view of `array`
             except Exception:
                 pass
+            if self.rank == 0:
+                try:  # on its own: the segment must go away whatever close() did
+                    self.shm.unlink()
+                except Exception:
+                    pass
             self.shm = None
 
 

@@ -477,13 +477,13 @@ class Image:
 class Scene:
     """Scene (src/scene.rs:21-25).  Scene.new flattens and uploads (BVH build happens in the library)."""
 
-    def __init__(self, nodes, lights, background=(1.0, 1.0, 1.0), device=0, upload=True, builder="sah"):
+    def __init__(self, nodes, lights, background=(1.0, 1.0, 1.0), device=0, upload=True, builder=None):
         self.nodes = list(nodes)
         self._lights = list(lights)
         self.background = tuple(float(x) for x in background)
         self.flat = FlatScene(self.nodes, self._lights, self.background)
         self.device = device
-        self.builder = builder  # "sah" (host binned SAH, default) or "lbvh" (device build)
+        self.builder = builder  # "sah" (host binned SAH) or "lbvh" (device build); None: library default / env NRB_BUILDER
         self._handle = None
         if upload:
             self.upload()
@@ -495,8 +495,11 @@ class Scene:
 
         lib = _lib.load()
         h = C.c_void_p()
-        opts = A.NrbBuildOptions(A.NRB_BUILDER_LBVH if self.builder == "lbvh" else A.NRB_BUILDER_SAH)
-        _lib.check(lib.nrb_scene_create_opts(C.byref(self.flat.desc), int(self.device), C.byref(opts), C.byref(h)))
+        if self.builder is None:
+            _lib.check(lib.nrb_scene_create_opts(C.byref(self.flat.desc), int(self.device), None, C.byref(h)))
+        else:
+            opts = A.NrbBuildOptions(A.NRB_BUILDER_LBVH if self.builder == "lbvh" else A.NRB_BUILDER_SAH)
+            _lib.check(lib.nrb_scene_create_opts(C.byref(self.flat.desc), int(self.device), C.byref(opts), C.byref(h)))
         self._handle = h
 
     def build_info(self):

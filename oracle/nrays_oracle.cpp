@@ -18,14 +18,19 @@
  *     rand 0.5 (Cargo.toml:14): rand::random (OS seeded, unreproducible).
  * Each function cites the reference file:line or the SURVEY.md Appendix B item it follows.
  *
- * PARITY UNPINNED.  The reference ships no test, golden image or known-answer vector
- * (SURVEY.md §4), cannot be compiled in this environment (no rustc/cargo, no vendored crates,
- * no network) and ncollide3d's source is absent, so nothing from the reference pins this
- * oracle.  Its own pins (tests/test_oracle_*.py) are closed-form known answers per primitive,
- * the Random123 Philox known-answer vectors, and f64-vs-f32 self-consistency.
+ * PARITY UNPINNED BY THE REFERENCE.  The reference ships no test, golden image or known-answer
+ * vector, cannot be compiled in this environment (no rustc/cargo, no vendored
+ * crates, no network) and ncollide3d's source is absent, so nothing from the reference pins this
+ * oracle.  Its own pins: closed-form known answers per primitive and the Random123 Philox
+ * known-answer vectors (tests/test_oracle_*.py), f64-vs-f32 self-consistency, and — since round 2 —
+ * an INDEPENDENT brute-force second implementation (tests/bruteforce.py: no BVT, no shared code,
+ * different intersection formulas, reads the host Scene objects instead of the flattened tables)
+ * that must agree with nro_cast / nro_intersects_ray / nro_trace / nro_render on randomised
+ * scenes (tests/test_bruteforce_pin.py).  That pins the implementation of SURVEY Appendix A+B;
+ * it cannot pin Appendix B's reading of ncollide3d itself.
  *
  * Deliberate, documented deviations from the reference:
- *   D1  RNG: rand::random is replaced by counter-based Philox4x32-10 keyed by (seed, stream) with
+ *   D1  RNG: rand::random is replaced by counter-based Philox4x32-10 keyed by (seed, stream ^ (depth/32)*phi) with
  *       counter (pixel, sample, path, light<<16|k); uniforms carry 24 bits ((x>>8)*2^-24) so the
  *       f32 device draws the identical value.  With window_width = 0 and light radius = 0 the
  *       render is RNG-free and this deviation vanishes.
@@ -917,7 +922,8 @@ struct Scene {
       for (uint32_t k = 0; k < ns; ++k) {
         // Light::sample — src/light.rs:56-63: pos + random::<Vect>() * radius  (D1 for the RNG)
         uint32_t ctr[4] = {ctx.pixel, ctx.sample, ctx.path, ((uint32_t)li << 16) | (k & 0xFFFFu)};
-        uint32_t key[2] = {(uint32_t)ctx.seed, (uint32_t)(ctx.seed >> 32) ^ STREAM_LIGHT};
+        // path doubles per bounce and wraps after 32 of them: the key takes depth / 32 so deeper paths keep their own streams
+        uint32_t key[2] = {(uint32_t)ctx.seed, (uint32_t)(ctx.seed >> 32) ^ STREAM_LIGHT ^ ((ctx.depth >> 5) * 0x9E3779B9u)};
         uint32_t rnd[4];
         philox4x32_10(ctr, key, rnd);
         V3<T> pos = light.pos + V3<T>((T)u24(rnd[0]), (T)u24(rnd[1]), (T)u24(rnd[2])) * light.radius;

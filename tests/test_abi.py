@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_c():
     structs = ["NrbNodeDesc", "NrbLightDesc", "NrbMaterialDesc", "NrbTextureDesc", "NrbSceneDesc", "NrbCamera",
-               "NrbTileSet", "NrbStats"]
+               "NrbTileSet", "NrbStats", "NrbBuildInfo", "NrbBuildOptions", "NrbIpcHandle"]
     prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "%s"' % HEADER, "int main(void){"]
     for s in structs:
         prog.append('printf("%s %%zu\\n", sizeof(%s));' % (s, s))

@@ -398,6 +398,24 @@ def test_both_children_spill_and_area_light(gpu):
     assert st.rays_reflect > 0 and st.rays_refract > 0
 
 
+def test_tail_spill_bound_with_weak_attenuation(gpu):
+    """Facing semi-transparent reflective panes with refl_atenuation 0.05: one chain reflects up to 19 times and spills a
+    refraction ray at every bounce (the old 4x heuristic overflowed here).  The spill queue is now sized by the
+    exact bound, and the frame matches the oracle with the tail phase forced on."""
+    pane = phong(ka=(0.15, 0.2, 0.25), kd=(0.4, 0.4, 0.4))
+    nodes = [node(Cuboid((1.6, 1.2, 0.05)), pane, pos=(0, 0, 1.0), alpha=0.5, refr=1.0, refl=(0.6, 0.05)),
+             node(Cuboid((1.6, 1.2, 0.05)), pane, pos=(0, 0, -1.0), alpha=0.5, refr=1.0, refl=(0.6, 0.05)),
+             node(Ball(0.4), phong(ka=(0.3, 0.1, 0.1)), pos=(0.2, 0.1, 0.0)),
+             node(Plane((0, 1, 0)), phong(), pos=(0, -1.3, 0))]
+    lights = [Light((0.5, 3.0, -4.0), 0.0, 1, (1, 1, 1))]
+    for env in (dict(NRB_TAIL_RAYS=1 << 30, NRB_TAIL_MIN_WAVE=1), dict(NRB_TAIL_RAYS=1 << 30, NRB_TAIL_MIN_WAVE=1, NRB_SPILL_CAP=1000), dict()):
+        with _Env(**env):
+            img, st, ref, ost = render_both(nodes, lights, eye=(0.3, 0.4, -4.5), w=96, h=72, spp=1, window=0.0, max_depth=40)
+        assert_parity(img, ref, what="weak attenuation panes %r" % (env,), wh=(96, 72))
+        assert_counts_close(st, ost, rel=5e-3)
+        assert st.rays_reflect > 10 * 96 * 72 / 4 and st.rays_refract > st.rays_reflect / 2
+
+
 @pytest.mark.parametrize("env", [dict(NRB_TAIL_RAYS=0), dict(NRB_TAIL_RAYS=1 << 30), dict(NRB_SHADOW_CAP=4096),
                                  dict(NRB_BATCH_SLOTS=4096), dict(NRB_BATCH_SLOTS=4096, NRB_SHADOW_CAP=2048, NRB_TAIL_RAYS=64),
                                  dict(NRB_REVERSE_SHADOW=0),
