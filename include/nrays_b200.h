@@ -213,8 +213,11 @@ int nrb_scene_validate(const NrbSceneDesc *desc, NrbBuildInfo *info);
 /* BVH builders.  The tree shape never changes render results, only build and traversal cost. */
 enum {
   NRB_BUILDER_SAH = 0, /* host binned-SAH build (threaded): best traversal, default */
-  NRB_BUILDER_LBVH = 1 /* device build (Morton sort + Karras radix tree + bottom-up fit): ~100x faster to build,
-                          slower to traverse — for one-shot renders of large meshes / dynamic scenes */
+  NRB_BUILDER_LBVH = 1, /* device build (Morton sort + Karras radix tree + bottom-up fit): fastest to build, slowest to
+                           traverse (the topology follows Morton prefixes, not the SAH) */
+  NRB_BUILDER_PLOC = 2  /* device build (Morton sort + parallel locally-ordered clustering, Meister & Bittner 2018): every merge
+                           minimises the merged surface area, so the tree traverses close to the SAH tree while still building
+                           in milliseconds — the device builder of choice for one-shot renders of large meshes */
 };
 typedef struct NrbBuildOptions {
   uint32_t builder; /* NRB_BUILDER_* */
@@ -270,6 +273,14 @@ int nrb_render_tiles_to_image(NrbScene *scene, const NrbCamera *camera, const Nr
  * otherwise NRB_ERR_UNSUPPORTED and the caller uses nrb_render_tiles_to_image. */
 int nrb_render_tiles_to_host(NrbScene *scene, const NrbCamera *camera, const NrbTileSet *tiles, float *host_image_rgb,
                              NrbStats *stats);
+
+/* RGB8 forms of the two exchanges above ("next" row 8f-2 fused into the exchange): the finished pixels leave the GPU quantised
+ * as Image::to_png encodes them (src/image.rs:64-77: clamp(c*255, 0, 255) truncated), 3 bytes per pixel instead of 12 over
+ * NVLink / PCIe.  `d_image_rgb8` / `host_image_rgb8`: width*height*3 bytes, row-major; same geometry rules as the float forms. */
+int nrb_render_tiles_to_image_rgb8(NrbScene *scene, const NrbCamera *camera, const NrbTileSet *tiles, uint8_t *d_image_rgb8,
+                                   NrbStats *stats);
+int nrb_render_tiles_to_host_rgb8(NrbScene *scene, const NrbCamera *camera, const NrbTileSet *tiles, uint8_t *host_image_rgb8,
+                                  NrbStats *stats);
 
 /* Device memory that other processes on the node can map (one process per GPU): the owner allocates and
  * passes the 64-byte handle around (any transport), peers open it and get a pointer valid in their kernels. */

@@ -193,6 +193,7 @@ class NrbBuildOptions(C.Structure):
 
 NRB_BUILDER_SAH = 0
 NRB_BUILDER_LBVH = 1
+NRB_BUILDER_PLOC = 2
 
 
 # Every symbol include/nrays_b200.h declares (tests check the .so exports all of them).
@@ -210,6 +211,8 @@ EXPORTS = [
     "nrb_render_tiles_device",
     "nrb_render_tiles_to_image",
     "nrb_render_tiles_to_host",
+    "nrb_render_tiles_to_image_rgb8",
+    "nrb_render_tiles_to_host_rgb8",
     "nrb_ipc_alloc",
     "nrb_ipc_open",
     "nrb_ipc_close",

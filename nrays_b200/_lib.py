@@ -54,6 +54,10 @@ def load():
     lib.nrb_render_tiles_to_image.restype = C.c_int
     lib.nrb_render_tiles_to_host.argtypes = [vp, C.POINTER(A.NrbCamera), C.POINTER(A.NrbTileSet), vp, C.POINTER(A.NrbStats)]
     lib.nrb_render_tiles_to_host.restype = C.c_int
+    lib.nrb_render_tiles_to_image_rgb8.argtypes = [vp, C.POINTER(A.NrbCamera), C.POINTER(A.NrbTileSet), vp, C.POINTER(A.NrbStats)]
+    lib.nrb_render_tiles_to_image_rgb8.restype = C.c_int
+    lib.nrb_render_tiles_to_host_rgb8.argtypes = [vp, C.POINTER(A.NrbCamera), C.POINTER(A.NrbTileSet), vp, C.POINTER(A.NrbStats)]
+    lib.nrb_render_tiles_to_host_rgb8.restype = C.c_int
     lib.nrb_ipc_alloc.argtypes = [C.c_int, C.c_uint64, C.POINTER(vp), C.POINTER(A.NrbIpcHandle)]
     lib.nrb_ipc_alloc.restype = C.c_int
     lib.nrb_ipc_open.argtypes = [C.c_int, C.POINTER(A.NrbIpcHandle), C.POINTER(vp)]

@@ -86,7 +86,7 @@ struct NrbScene {
   bool has_nmap = false;  // some node carries a depth-shift texture: general trace kernel (kernels.cu: trace_general_kernel)
   int child_factor = 0;  // max secondary rays per ray (reflection + refraction possible in this scene)
   uint32_t refl_chain_max = 0;  // most reflections one ray chain can make before its energy is spent (0xFFFFFFFF: unbounded)
-  uint64_t n_bvh_nodes = 0, n_tris = 0, scene_bytes = 0;
+  uint64_t n_bvh_nodes = 0, n_tris = 0, scene_bytes = 0, node_bytes = 64;
   int grid_trace = 148, grid_tail = 148;
   NrbBuildInfo build_info{};
   // frame state
@@ -187,7 +187,19 @@ struct HostScene {
   float gpu_build_ms = 0.0f;  // device time of the LBVH kernels (NRB_BUILDER_LBVH)
 };
 
+struct PhaseTimer {  // NRB_BUILD_TIMES=1: per-phase host times of Scene::new on stderr
+  bool on = getenv("NRB_BUILD_TIMES") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char *what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[nrb] build: %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BUILDER_SAH) {
+  PhaseTimer pt;
   if (d.n_nodes && !d.nodes) return fail(NRB_ERR_INVALID_ARG, "nodes is NULL");
   if (d.n_lights && !d.lights) return fail(NRB_ERR_INVALID_ARG, "lights is NULL");
   if (d.n_materials && !d.materials) return fail(NRB_ERR_INVALID_ARG, "materials is NULL");
@@ -350,6 +362,7 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
       }
     }
   }
+  pt.lap("triangles to world space");
   // shape boxes (bounding_volume(&transform), src/scene_node.rs:41), conservative
   std::vector<Box> shape_box(shapes.size());
   for (size_t si = 0; si < shapes.size(); ++si) {
@@ -399,15 +412,17 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
   std::vector<BuildItem> opaque_items, top_items;
   // builds one tree over a set of triangles with the selected builder and appends it to the shared pools
   auto build_set = [&](std::vector<BuildItem> &items, Box *rb, int *code) -> int {
-    if (builder == NRB_BUILDER_LBVH) {
+    if (builder == NRB_BUILDER_LBVH || builder == NRB_BUILDER_PLOC) {
       std::vector<Box> boxes(items.size());
       for (size_t k = 0; k < items.size(); ++k) boxes[k] = items[k].box;
       std::vector<BvhNode> sub;
       std::vector<uint32_t> order;
       int depth = 0, root = kEmpty;
       float ms = 0.0f;
-      cudaError_t e = lbvh_build(boxes.data(), (uint32_t)boxes.size(), sub, order, &root, rb, &depth, &ms);
-      if (e != cudaSuccess) return fail(NRB_ERR_CUDA, std::string("lbvh_build: ") + cudaGetErrorString(e));
+      cudaError_t e = builder == NRB_BUILDER_PLOC
+                          ? ploc_build(boxes.data(), (uint32_t)boxes.size(), (int)env_size("NRB_PLOC_RADIUS", 16), sub, order, &root, rb, &depth, &ms)
+                          : lbvh_build(boxes.data(), (uint32_t)boxes.size(), sub, order, &root, rb, &depth, &ms);
+      if (e != cudaSuccess) return fail(NRB_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString(e));
       H.gpu_build_ms += ms;
       const int node_off = (int)bb.nodes.size();
       const uint32_t tri_off = (uint32_t)bb.tri_order.size();
@@ -444,6 +459,7 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
       opaque_items.push_back(BuildItem{rb, code});
     }
   }
+  pt.lap("opaque triangle tree");
   int depth_tri = bb.max_depth_seen;
   std::vector<Candidate> candidates, nmaps;
   for (uint32_t i = 0; i < d.n_nodes; ++i) {
@@ -532,12 +548,15 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
   if (depth_tri + depth_mid + depth_top + 4 > kStackSize)
     return fail(NRB_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
   if (nmaps.size() > 32) return fail(NRB_ERR_UNSUPPORTED, "more than 32 nodes with a depth-shift (nmap) texture");
+  pt.lap("candidate / top trees");
   relayout_bfs(bb.nodes, root_all, root_opaque, candidates, nmaps);
+  pt.lap("level-order relayout");
 
   // leaf-ordered triangle arrays
   H.tris.resize(bb.tri_order.size());
   H.tri_uvs.resize(bb.tri_order.size());
   for (size_t k = 0; k < bb.tri_order.size(); ++k) H.tris[k] = tris_in[bb.tri_order[k]], H.tri_uvs[k] = uvs_in[bb.tri_order[k]];
+  pt.lap("leaf-ordered triangle arrays");
   H.nodes.swap(bb.nodes);
   H.shapes.swap(shapes);
   H.node_info.swap(node_info);
@@ -607,55 +626,134 @@ int check_bvh(const HostScene &H, std::string &why) {
   return 0;
 }
 
-// Device node format: box centres + half extents (see device_types.cuh).  The half extent is rounded
-// up so the device box contains the builder's [lo, hi] box.
-std::vector<BvhNode> to_centre_half(const std::vector<BvhNode> &in) {
-  std::vector<BvhNode> out(in.size());
-  for (size_t i = 0; i < in.size(); ++i) {
-    const BvhNode &n = in[i];
-    const float lo[2][3] = {{n.n0.x, n.n0.z, n.n2.x}, {n.n1.x, n.n1.z, n.n2.z}};
-    const float hi[2][3] = {{n.n0.y, n.n0.w, n.n2.y}, {n.n1.y, n.n1.w, n.n2.w}};
-    float c[2][3], h[2][3];
-    for (int b = 0; b < 2; ++b)
-      for (int k = 0; k < 3; ++k) {
-        float l = std::max(lo[b][k], -1.0e30f), u = std::min(hi[b][k], 1.0e30f);
-        float cc = 0.5f * l + 0.5f * u;
-        float hh = std::max(u - cc, cc - l);
-        hh = hh * 1.0000005f + std::fabs(cc) * 1.2e-7f + 1e-30f;  // covers the rounding of cc and of u - cc
-        c[b][k] = cc;
-        h[b][k] = hh;
-      }
-    BvhNode &o = out[i];
-    o.n0 = make_float4(c[0][0], c[0][1], c[0][2], c[1][0]);
-    o.n1 = make_float4(c[1][1], c[1][2], h[0][0], h[0][1]);
-    o.n2 = make_float4(h[0][2], h[1][0], h[1][1], h[1][2]);
-    o.n3 = n.n3;
-  }
-  return out;
+// Device node formats: box centres + half extents (device_types.cuh "node formats").  The half extent is rounded up so
+// the device box contains the builder's [lo, hi] box — in fp32 for format 0, to bf16 for format 2.
+struct DevNodes {
+  std::vector<float> a;  // 16 words per node, every format (format 2 uses the first 12)
+};
+
+struct NodeBoxes {  // one node's two child boxes as (centre, half extent), plus the child codes
+  float c[2][3], h[2][3];
+  int ch[2];
+};
+
+float bf16_round_up(float v) {  // smallest bf16 >= v for v >= 0
+  uint32_t u;
+  std::memcpy(&u, &v, 4);
+  if (u & 0xFFFFu) u = (u | 0xFFFFu) + 1u;
+  u &= 0xFFFF0000u;
+  float r;
+  std::memcpy(&r, &u, 4);
+  return r;
+}
+uint32_t bf16_pair(float lo, float hi) {  // two bf16-exact floats -> one word (lo in the low half)
+  uint32_t a, b;
+  std::memcpy(&a, &lo, 4);
+  std::memcpy(&b, &hi, 4);
+  return (a >> 16) | (b & 0xFFFF0000u);
 }
 
-// The device boxes (centre -+ half extent, evaluated in f32 as the kernel sees them) must contain the builder's boxes.
+NodeBoxes centre_half(const BvhNode &n, int format) {
+  const float lo[2][3] = {{n.n0.x, n.n0.z, n.n2.x}, {n.n1.x, n.n1.z, n.n2.z}};
+  const float hi[2][3] = {{n.n0.y, n.n0.w, n.n2.y}, {n.n1.y, n.n1.w, n.n2.w}};
+  NodeBoxes o;
+  for (int b = 0; b < 2; ++b)
+    for (int k = 0; k < 3; ++k) {
+      float l = std::max(lo[b][k], -1.0e30f), u = std::min(hi[b][k], 1.0e30f);
+      float cc = 0.5f * l + 0.5f * u;
+      float hh = std::max(u - cc, cc - l);
+      hh = hh * 1.0000005f + std::fabs(cc) * 1.2e-7f + 1e-30f;  // covers the rounding of cc and of u - cc
+      if (format == 2) hh = bf16_round_up(hh);
+      o.c[b][k] = cc;
+      o.h[b][k] = hh;
+    }
+  o.ch[0] = n.n3.x, o.ch[1] = n.n3.y;
+  return o;
+}
+
+DevNodes to_device_nodes(const std::vector<BvhNode> &in, int format) {
+  DevNodes d;
+  const size_t wa = 16;
+  d.a.assign(in.size() * wa, 0.0f);
+  auto put_int = [](float *dst, int v) { std::memcpy(dst, &v, 4); };
+  auto put_u32 = [](float *dst, uint32_t v) { std::memcpy(dst, &v, 4); };
+  for (size_t i = 0; i < in.size(); ++i) {
+    const NodeBoxes nb = centre_half(in[i], format);
+    float *o = &d.a[i * wa];
+    if (format == 0) {
+      const float rec[12] = {nb.c[0][0], nb.c[0][1], nb.c[0][2], nb.c[1][0], nb.c[1][1], nb.c[1][2],
+                             nb.h[0][0], nb.h[0][1], nb.h[0][2], nb.h[1][0], nb.h[1][1], nb.h[1][2]};
+      std::memcpy(o, rec, sizeof(rec));
+      put_int(o + 12, nb.ch[0]), put_int(o + 13, nb.ch[1]);
+    } else {
+      const float rec[6] = {nb.c[0][0], nb.c[0][1], nb.c[1][0], nb.c[1][1], nb.c[0][2], nb.c[1][2]};
+      std::memcpy(o, rec, sizeof(rec));
+      put_u32(o + 6, bf16_pair(nb.h[0][0], nb.h[0][1]));
+      put_u32(o + 7, bf16_pair(nb.h[1][0], nb.h[1][1]));
+      float *ob = o + 8;
+      put_u32(ob, bf16_pair(nb.h[0][2], nb.h[1][2]));
+      put_int(ob + 1, nb.ch[0]), put_int(ob + 2, nb.ch[1]);
+    }
+  }
+  return d;
+}
+
+// Decodes node i of a device array back into (centre, half extent) exactly as the kernel reads it.
+NodeBoxes decode_device_node(const DevNodes &d, size_t i, int format) {
+  NodeBoxes o;
+  auto get_int = [](const float *src) { int v; std::memcpy(&v, src, 4); return v; };
+  auto bf_lo = [](const float *src) { uint32_t u; std::memcpy(&u, src, 4); u <<= 16; float r; std::memcpy(&r, &u, 4); return r; };
+  auto bf_hi = [](const float *src) { uint32_t u; std::memcpy(&u, src, 4); u &= 0xFFFF0000u; float r; std::memcpy(&r, &u, 4); return r; };
+  if (format == 0) {
+    const float *p = &d.a[i * 16];
+    for (int k = 0; k < 3; ++k) o.c[0][k] = p[k], o.c[1][k] = p[3 + k], o.h[0][k] = p[6 + k], o.h[1][k] = p[9 + k];
+    o.ch[0] = get_int(p + 12), o.ch[1] = get_int(p + 13);
+  } else {
+    const float *p = &d.a[i * 16], *q = p + 8;
+    o.c[0][0] = p[0], o.c[0][1] = p[1], o.c[1][0] = p[2], o.c[1][1] = p[3], o.c[0][2] = p[4], o.c[1][2] = p[5];
+    o.h[0][0] = bf_lo(p + 6), o.h[0][1] = bf_hi(p + 6), o.h[1][0] = bf_lo(p + 7), o.h[1][1] = bf_hi(p + 7);
+    o.h[0][2] = bf_lo(q), o.h[1][2] = bf_hi(q);
+    o.ch[0] = get_int(q + 1), o.ch[1] = get_int(q + 2);
+  }
+  return o;
+}
+
+// The device boxes (centre -+ half extent, evaluated in f32 as the kernel sees them) must contain the builder's boxes —
+// for EVERY node format, whichever one the kernels were compiled for.
 int check_device_nodes(const HostScene &H, std::string &why) {
-  const std::vector<BvhNode> dev = to_centre_half(H.nodes);
-  for (size_t i = 0; i < H.nodes.size(); ++i) {
-    const BvhNode &n = H.nodes[i], &d = dev[i];
-    const float lo[2][3] = {{n.n0.x, n.n0.z, n.n2.x}, {n.n1.x, n.n1.z, n.n2.z}};
-    const float hi[2][3] = {{n.n0.y, n.n0.w, n.n2.y}, {n.n1.y, n.n1.w, n.n2.w}};
-    const float c[2][3] = {{d.n0.x, d.n0.y, d.n0.z}, {d.n0.w, d.n1.x, d.n1.y}};
-    const float h[2][3] = {{d.n1.z, d.n1.w, d.n2.x}, {d.n2.y, d.n2.z, d.n2.w}};
-    for (int b = 0; b < 2; ++b)
-      for (int k = 0; k < 3; ++k) {
-        const float l = std::max(lo[b][k], -1.0e30f), u = std::min(hi[b][k], 1.0e30f);
-        if (!(c[b][k] - h[b][k] <= l) || !(c[b][k] + h[b][k] >= u) || !(h[b][k] >= 0.0f))
-          return why = "device box (centre / half extent) does not contain the builder's box", 1;
-      }
-    if (d.n3.x != n.n3.x || d.n3.y != n.n3.y) return why = "device node lost its child codes", 1;
+  for (int format = 0; format <= 2; format += 2) {
+    const DevNodes dev = to_device_nodes(H.nodes, format);
+    for (size_t i = 0; i < H.nodes.size(); ++i) {
+      const BvhNode &n = H.nodes[i];
+      const NodeBoxes d = decode_device_node(dev, i, format);
+      const float lo[2][3] = {{n.n0.x, n.n0.z, n.n2.x}, {n.n1.x, n.n1.z, n.n2.z}};
+      const float hi[2][3] = {{n.n0.y, n.n0.w, n.n2.y}, {n.n1.y, n.n1.w, n.n2.w}};
+      for (int b = 0; b < 2; ++b)
+        for (int k = 0; k < 3; ++k) {
+          const float l = std::max(lo[b][k], -1.0e30f), u = std::min(hi[b][k], 1.0e30f);
+          if (!(d.c[b][k] - d.h[b][k] <= l) || !(d.c[b][k] + d.h[b][k] >= u) || !(d.h[b][k] >= 0.0f))
+            return why = "device box (centre / half extent, node format " + std::to_string(format) + ") does not contain the builder's box", 1;
+        }
+      if (d.ch[0] != n.n3.x || d.ch[1] != n.n3.y) return why = "device node lost its child codes", 1;
+    }
   }
   return 0;
 }
 
 int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
-  CU(upload(S.d_nodes, to_centre_half(H.nodes)));
+  // Node format (device_types.cuh): scenes that fit L2 keep full fp32 boxes; scenes larger than L2 — where rays diverge and
+  // every lane fetches its own cache line — use the 48-byte-per-visit bf16 form.  Depth-shift (nmap) scenes run the general
+  // kernel, compiled for format 0 only.  NRB_NODE_FORMAT=0|2 overrides (experiments).
+  const uint64_t geom_bytes = H.nodes.size() * 64ull + H.tris.size() * sizeof(Tri);
+  int nfmt = (geom_bytes > (96ull << 20) && H.nmaps.empty()) ? 2 : 0;
+  if (const char *e = getenv("NRB_NODE_FORMAT")) {
+    const int f = atoi(e);
+    if ((f == 0 || f == 2) && (H.nmaps.empty() || f == 0)) nfmt = f;
+  }
+  {
+    const DevNodes dn = to_device_nodes(H.nodes, nfmt);
+    CU(upload(S.d_nodes, dn.a));
+  }
   CU(upload(S.d_tris, H.tris));
   CU(upload(S.d_tri_uvs, H.tri_uvs));
   CU(upload(S.d_shapes, H.shapes));
@@ -672,7 +770,8 @@ int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
     if (d.n_texels) CU(cudaMemcpy(S.d_texels.p, d.texels, d.n_texels * 16, cudaMemcpyHostToDevice));
   }
   SceneView &v = S.view;
-  v.nodes = S.d_nodes.as<BvhNode>();
+  v.nodes = S.d_nodes.p;
+  v.node_format = nfmt;
   v.tris = S.d_tris.as<Tri>();
   v.tri_uvs = S.d_tri_uvs.as<TriUV>();
   v.shapes = S.d_shapes.as<Shape>();
@@ -698,7 +797,8 @@ int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
   S.refl_chain_max = H.refl_chain_max;
   S.n_bvh_nodes = H.nodes.size();
   S.n_tris = H.tris.size();
-  S.scene_bytes = H.nodes.size() * sizeof(BvhNode) + H.tris.size() * (sizeof(Tri) + sizeof(TriUV)) +
+  S.node_bytes = 64;  // stride; format 2 reads 48 of them per visit
+  S.scene_bytes = H.nodes.size() * S.node_bytes + H.tris.size() * (sizeof(Tri) + sizeof(TriUV)) +
                   H.shapes.size() * sizeof(Shape) + d.n_texels * 16;
   return NRB_OK;
 }
@@ -791,7 +891,7 @@ cudaEvent_t get_event(NrbScene &S, size_t &used) {
 // changed straight into the host image once that copy has landed.  *early_used tells the caller which happened.
 int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, float *d_out, uint8_t *d_out8,
                   uint32_t *n_local_tiles, NrbStats *stats, bool to_image = false, float *early_h_out = nullptr,
-                  float *early_d_out = nullptr, bool *early_used = nullptr, float *segments_h_out = nullptr) {
+                  float *early_d_out = nullptr, bool *early_used = nullptr, void *segments_h_out = nullptr) {
   CU(cudaSetDevice(S.device));
   FrameParams fp;
   int rc = make_frame_params(cam, tiles, fp);
@@ -1059,7 +1159,16 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   if (early_used && *early_used) {
     CU(cudaStreamWaitEvent(st, S.ev_copied, 0));  // the early image must have landed before its pixels are overwritten
     launch_patch_host_image(accum, d_out, n_acc, fp.spp, early_d_out, st);
-  } else if (d_out8)
+  } else if (segments_h_out && fp.packed && d_out8) {
+    // RGB8 form: 48-byte segments
+    const uint32_t cols_per_rank = fp.tiles_x / fp.tile_stride;
+    launch_resolve_tiles_to_segments_rgb8(accum, fp, cols_per_rank, d_out8, st);
+    const size_t seg = (size_t)NRB_TILE * 3;
+    CU(cudaMemcpy2DAsync((char *)segments_h_out + (size_t)fp.tile_first * seg, (size_t)fp.tile_stride * seg, d_out8, seg, seg,
+                         (size_t)fp.height * cols_per_rank, cudaMemcpyDeviceToHost, st));
+  } else if (to_image && fp.packed && d_out8)
+    launch_resolve_tiles_to_image_rgb8(accum, fp, d_out8, st);
+  else if (d_out8)
     launch_resolve_rgb8(accum, n_acc, fp.spp, d_out8, st);
   else if (segments_h_out && fp.packed) {
     // this rank's tile columns as back-to-back 192-byte segments, then ONE strided 2-D DMA into the shared host image
@@ -1168,9 +1277,10 @@ int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOp
   if (!desc || !out) return fail(NRB_ERR_INVALID_ARG, "desc/out is NULL");
   uint32_t builder = opts ? opts->builder : NRB_BUILDER_SAH;
   if (!opts) {  // the environment only fills in for a caller that expressed no choice
-    if (const char *e = getenv("NRB_BUILDER")) builder = (std::string(e) == "lbvh") ? NRB_BUILDER_LBVH : NRB_BUILDER_SAH;
+    if (const char *e = getenv("NRB_BUILDER"))
+      builder = (std::string(e) == "lbvh") ? NRB_BUILDER_LBVH : (std::string(e) == "ploc") ? NRB_BUILDER_PLOC : NRB_BUILDER_SAH;
   }
-  if (builder != NRB_BUILDER_SAH && builder != NRB_BUILDER_LBVH) return fail(NRB_ERR_INVALID_ARG, "unknown builder");
+  if (builder != NRB_BUILDER_SAH && builder != NRB_BUILDER_LBVH && builder != NRB_BUILDER_PLOC) return fail(NRB_ERR_INVALID_ARG, "unknown builder");
   if (desc->struct_size != sizeof(NrbSceneDesc) || desc->abi_version != NRB_ABI_VERSION)
     return fail(NRB_ERR_INVALID_ARG, "NrbSceneDesc struct_size / abi_version mismatch");
   int ndev = nrb_device_count();
@@ -1349,6 +1459,27 @@ int nrb_render_tiles_to_host(NrbScene *scene, const NrbCamera *camera, const Nrb
   CU(scene->d_out.ensure(std::max<size_t>(local_px * 3 * sizeof(float), 16)));
   return render_device(*scene, *camera, tiles, scene->d_out.as<float>(), nullptr, nullptr, stats, false, nullptr, nullptr, nullptr,
                        host_image_rgb);
+}
+
+int nrb_render_tiles_to_image_rgb8(NrbScene *scene, const NrbCamera *camera, const NrbTileSet *tiles, uint8_t *d_image_rgb8,
+                                   NrbStats *stats) {
+  if (!scene || !camera || !tiles || !d_image_rgb8) return fail(NRB_ERR_INVALID_ARG, "scene/camera/tiles/image is NULL");
+  return render_device(*scene, *camera, tiles, nullptr, d_image_rgb8, nullptr, stats, true);
+}
+
+int nrb_render_tiles_to_host_rgb8(NrbScene *scene, const NrbCamera *camera, const NrbTileSet *tiles, uint8_t *host_image_rgb8,
+                                  NrbStats *stats) {
+  if (!scene || !camera || !tiles || !host_image_rgb8) return fail(NRB_ERR_INVALID_ARG, "scene/camera/tiles/image is NULL");
+  const uint32_t tiles_x = (camera->width + NRB_TILE - 1) / NRB_TILE;
+  if (tiles->stride == 0 || tiles->first >= tiles->stride || camera->width % NRB_TILE != 0 || tiles_x % tiles->stride != 0)
+    return fail(NRB_ERR_UNSUPPORTED, "tiles_to_host_rgb8 needs width % 16 == 0, tiles_x % stride == 0 and first < stride "
+                                     "(each rank then owns whole tile columns); use nrb_render_tiles_to_image_rgb8");
+  CU(cudaSetDevice(scene->device));
+  const uint32_t tiles_y = (camera->height + NRB_TILE - 1) / NRB_TILE;
+  const size_t local_px = (size_t)(tiles_x / tiles->stride) * tiles_y * NRB_TILE * NRB_TILE;
+  CU(scene->d_out8.ensure(std::max<size_t>(local_px * 3, 16)));
+  return render_device(*scene, *camera, tiles, nullptr, scene->d_out8.as<uint8_t>(), nullptr, stats, false, nullptr, nullptr, nullptr,
+                       host_image_rgb8);
 }
 
 int nrb_ipc_alloc(int device, uint64_t bytes, void **d_ptr, NrbIpcHandle *handle) {

@@ -16,9 +16,11 @@ namespace nrb {
 //   n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
 //   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
 //   n3 = (child0, child1, -, -) as int bits
-// The DEVICE copy is converted at upload (api.cu: to_centre_half) to centres + half extents, which turns
-// the slab test into 9 FFMA + 4 min/max per box (kernels.cu: test_children):
-//   n0 = (c0.centre.xyz, c1.centre.x)   n1 = (c1.centre.yz, c0.half.xy)   n2 = (c0.half.z, c1.half.xyz)   n3 as above
+// The DEVICE copy is converted at upload (api.cu: to_device_nodes) to centres + half extents, which turns
+// the slab test into 9 FFMA + 4 min/max per box (kernels.cu: test_children).  Node formats (SceneView.node_format, chosen per scene):
+//   0 (64 B): n0 = (c0.centre.xyz, c1.centre.x)   n1 = (c1.centre.yz, c0.half.xy)   n2 = (c0.half.z, c1.half.xyz)   n3 as above
+//   2 (48 B used, 64 B stride): (c0.cx, c0.cy, c1.cx, c1.cy) (c0.cz, c1.cz, bf16x2(c0.hx, c0.hy), bf16x2(c1.hx, c1.hy))
+//             (bf16x2(c0.hz, c1.hz), child0, child1, -) (unused); half extents rounded UP to bf16
 // Child code c:  c >= 0 -> inner node index;  c < 0 -> leaf, ~c = (first << 3) | ((count-1) << 1) | is_shape
 //   is_shape = 0: triangles [first, first+count) of the leaf-ordered triangle array (count <= 4)
 //   is_shape = 1: analytic shape `first` of the shape table (count == 1)
@@ -105,7 +107,8 @@ struct Candidate {
 };
 
 struct SceneView {
-  const BvhNode *nodes;
+  const void *nodes;    // device node records, 64-byte stride
+  int node_format;      // 0: fp32 centres + half extents (64 B read per visit); 2: bf16 half extents (48 B read per visit)
   const Tri *tris;
   const TriUV *tri_uvs;
   const Shape *shapes;

@@ -95,16 +95,52 @@ struct Hit {
   float u, v;
 };
 
-// One 64-byte node record (device_types.cuh): centres + half extents of both children, child codes.
-struct NodeRec {
+// One node record as the traversal loop sees it (device_types.cuh "node formats").  Two formats are compiled and the scene
+// picks one at creation (api.cu):
+//   format 0: 64 bytes, two 256-bit loads — the fastest form while the scene lives in L2 and neighbouring rays visit the same
+//             nodes (C3: 2.34 ms vs 2.43 ms for format 2).
+//   format 2: 48 bytes used of a 64-byte record: the six half extents are stored as bf16 (rounded up: the box only grows, by
+//             < 0.8 % of its half extent), fetched with one 256-bit + one 128-bit load and unpacked with 6 shifts / masks.
+//             Fewer bytes per visit pay when rays diverge and every lane fetches its own line (C4 hairball: 8.28 ms vs
+//             8.91 ms).  The record keeps its 64-byte stride so a divergent lane still touches ONE cache line per visit.
+// Both run the slab test on the packed FP32 pipe form (FFMA2, PTX fma.rn.f32x2) where it is free: measured on B200 the
+// FFMA2 issues at half the FFMA rate (1.86 vs 3.88 warp-instructions / clk / SM, scripts/ubench_ffma2.cu), so it saves issue
+// slots but no FMA-pipe time, and on this loop it is neutral (format 1 = format 0 with FFMA2: 2.37 vs 2.34 ms on C3).
+// Format 0 therefore keeps the scalar FFMA form of round 1; format 2 uses FFMA2 (its operands arrive as pairs anyway).
+typedef unsigned long long u64;
+NRB_DI u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+NRB_DI void upk2(u64 r, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r)); }
+NRB_DI u64 fma2(u64 a, u64 b, u64 c) {  // FFMA2: two fp32 FMAs in one issue slot (sm_100+)
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+template <int FMT>
+struct NodeRec;
+template <>
+struct NodeRec<0> {
   float4 n0, n1, n2;
   int c0, c1;
 };
+template <>
+struct NodeRec<2> {
+  u64 cxy0, cxy1, cz01;  // (c0.x,c0.y) (c1.x,c1.y) (c0.z,c1.z)
+  u64 hxy0, hxy1, hz01;  // half extents, same pairing
+  int c0, c1;
+};
 
-NRB_DI NodeRec load_node(const SceneView &sc, int node) {
-  NodeRec r;
-  const BvhNode *np = sc.nodes + node;
-#if NRB_NODE_LOADS == 1
+template <int FMT>
+NRB_DI NodeRec<FMT> load_node(const SceneView &sc, int node);
+
+template <>
+NRB_DI NodeRec<0> load_node<0>(const SceneView &sc, int node) {
+  NodeRec<0> r;
+  const char *np = reinterpret_cast<const char *>(sc.nodes) + (size_t)(unsigned)node * 64u;
   // two 256-bit loads (LDG.E.256, sm_100+) fetch the whole record; the child codes arrive with the boxes
   int pad0, pad1;  // the record's two unused words
   (void)pad0, (void)pad1;
@@ -113,22 +149,24 @@ NRB_DI NodeRec load_node(const SceneView &sc, int node) {
                : "l"(np));
   asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(r.n2.x), "=f"(r.n2.y), "=f"(r.n2.z), "=f"(r.n2.w), "=r"(r.c0), "=r"(r.c1), "=r"(pad0), "=r"(pad1)
-               : "l"(reinterpret_cast<const char *>(np) + 32));
-#elif NRB_NODE_LOADS == 2
-  // 256 + 128 + 64 bits: only the 56 bytes in use cross the L1 data pipe
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(r.n0.x), "=f"(r.n0.y), "=f"(r.n0.z), "=f"(r.n0.w), "=f"(r.n1.x), "=f"(r.n1.y), "=f"(r.n1.z), "=f"(r.n1.w)
-               : "l"(np));
-  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(r.n2.x), "=f"(r.n2.y), "=f"(r.n2.z), "=f"(r.n2.w)
-               : "l"(reinterpret_cast<const char *>(np) + 32));
-  asm volatile("ld.global.nc.v2.b32 {%0,%1}, [%2];" : "=r"(r.c0), "=r"(r.c1) : "l"(reinterpret_cast<const char *>(np) + 48));
-#else
-  const float4 *fp4 = reinterpret_cast<const float4 *>(np);
-  r.n0 = __ldg(fp4), r.n1 = __ldg(fp4 + 1), r.n2 = __ldg(fp4 + 2);
-  int2 ch = __ldg(reinterpret_cast<const int2 *>(fp4 + 3));
-  r.c0 = ch.x, r.c1 = ch.y;
-#endif
+               : "l"(np + 32));
+  return r;
+}
+
+template <>
+NRB_DI NodeRec<2> load_node<2>(const SceneView &sc, int node) {
+  NodeRec<2> r;
+  const char *na = reinterpret_cast<const char *>(sc.nodes) + (size_t)(unsigned)node * 64u;
+  uint32_t wxy0, wxy1, wz, pad;
+  (void)pad;
+  u64 hw;
+  asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.cxy0), "=l"(r.cxy1), "=l"(r.cz01), "=l"(hw) : "l"(na));
+  asm volatile("ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(wz), "=r"(r.c0), "=r"(r.c1), "=r"(pad) : "l"(na + 32));
+  wxy0 = (uint32_t)hw, wxy1 = (uint32_t)(hw >> 32);
+  // bf16 pairs -> fp32 pairs: low half << 16, high half masked
+  r.hxy0 = pk2(__uint_as_float(wxy0 << 16), __uint_as_float(wxy0 & 0xFFFF0000u));
+  r.hxy1 = pk2(__uint_as_float(wxy1 << 16), __uint_as_float(wxy1 & 0xFFFF0000u));
+  r.hz01 = pk2(__uint_as_float(wz << 16), __uint_as_float(wz & 0xFFFF0000u));
   return r;
 }
 
@@ -148,7 +186,7 @@ NRB_DI RayPre ray_pre(V3 o, V3 d) {
 
 // Both children's slab tests in centre / half-extent form: t(centre) -+ half * |1/d| — 9 FFMA + 4
 // min/max per box and no lo/hi sort (the FMNMX pipe, not the FMA pipe, limits the classic form).
-NRB_DI void test_children(const NodeRec &n, const RayPre &p, float tbest, float &c0min, float &c0max, float &c1min,
+NRB_DI void test_children(const NodeRec<0> &n, const RayPre &p, float tbest, float &c0min, float &c0max, float &c1min,
                           float &c1max) {
   const float aidx = fabsf(p.idx), aidy = fabsf(p.idy), aidz = fabsf(p.idz);
   float c0tx = fmaf(n.n0.x, p.idx, -p.oodx), c0ty = fmaf(n.n0.y, p.idy, -p.oody), c0tz = fmaf(n.n0.z, p.idz, -p.oodz);
@@ -157,6 +195,27 @@ NRB_DI void test_children(const NodeRec &n, const RayPre &p, float tbest, float 
   c0max = fminf(fminf(fmaf(n.n1.z, aidx, c0tx), fmaf(n.n1.w, aidy, c0ty)), fminf(fmaf(n.n2.x, aidz, c0tz), tbest));
   c1min = fmaxf(fmaxf(fmaf(-n.n2.y, aidx, c1tx), fmaf(-n.n2.z, aidy, c1ty)), fmaxf(fmaf(-n.n2.w, aidz, c1tz), 0.0f));
   c1max = fminf(fminf(fmaf(n.n2.y, aidx, c1tx), fmaf(n.n2.z, aidy, c1ty)), fminf(fmaf(n.n2.w, aidz, c1tz), tbest));
+}
+// The same test on pairs: 9 FFMA2 + 8 min/max.  ptxas folds the |1/d| and -|1/d| operands into FFMA2's abs / neg modifiers
+// and the (1/d.z, 1/d.z) pair into its scalar-broadcast operand form, so the ray constants stay in six registers.
+NRB_DI void test_children(const NodeRec<2> &n, const RayPre &p, float tbest, float &c0min, float &c0max, float &c1min,
+                          float &c1max) {
+  const u64 idxy = pk2(p.idx, p.idy), idzz = pk2(p.idz, p.idz);
+  const u64 noodxy = pk2(-p.oodx, -p.oody), noodzz = pk2(-p.oodz, -p.oodz);
+  const u64 aidxy = pk2(fabsf(p.idx), fabsf(p.idy)), aidzz = pk2(fabsf(p.idz), fabsf(p.idz));
+  const u64 naidxy = pk2(-fabsf(p.idx), -fabsf(p.idy)), naidzz = pk2(-fabsf(p.idz), -fabsf(p.idz));
+  const u64 t0 = fma2(n.cxy0, idxy, noodxy), t1 = fma2(n.cxy1, idxy, noodxy), tz = fma2(n.cz01, idzz, noodzz);
+  float l0x, l0y, l1x, l1y, l0z, l1z, h0x, h0y, h1x, h1y, h0z, h1z;
+  upk2(fma2(n.hxy0, naidxy, t0), l0x, l0y);
+  upk2(fma2(n.hxy0, aidxy, t0), h0x, h0y);
+  upk2(fma2(n.hxy1, naidxy, t1), l1x, l1y);
+  upk2(fma2(n.hxy1, aidxy, t1), h1x, h1y);
+  upk2(fma2(n.hz01, naidzz, tz), l0z, l1z);
+  upk2(fma2(n.hz01, aidzz, tz), h0z, h1z);
+  c0min = fmaxf(fmaxf(l0x, l0y), fmaxf(l0z, 0.0f));
+  c0max = fminf(fminf(h0x, h0y), fminf(h0z, tbest));
+  c1min = fmaxf(fmaxf(l1x, l1y), fmaxf(l1z, 0.0f));
+  c1max = fminf(fminf(h1x, h1y), fminf(h1z, tbest));
 }
 
 // Slab test of one padded box [lo, hi] against the segment [0, tmax] with the ray's precomputed reciprocals — the
@@ -172,7 +231,7 @@ NRB_DI bool box_hit(const RayPre &p, const float lo[3], const float hi[3], float
 
 // ANY = true: return at the first hit with toi <= tmax (shadow rays vs opaque geometry).
 // ANY = false: closest hit with toi < tmax (strict, best_first_search keeps the first of equals).
-template <bool HAS_SHAPES, bool ANY>
+template <bool HAS_SHAPES, bool ANY, int FMT>
 NRB_DI bool traverse(const SceneView &sc, int root, V3 o, V3 d, float tmax, Hit &hit) {
   int stack[kStackSize];
   int sp = 0;
@@ -191,7 +250,7 @@ NRB_DI bool traverse(const SceneView &sc, int root, V3 o, V3 d, float tmax, Hit 
 #ifdef NRB_COUNT_VISITS
       ++dbg_n;
 #endif
-      const NodeRec n = load_node(sc, node);
+      const NodeRec<FMT> n = load_node<FMT>(sc, node);
       float c0min, c0max, c1min, c1max;
       test_children(n, pre, tbest, c0min, c0max, c1min, c1max);
       bool h0 = c0max >= c0min, h1 = c1max >= c1min;
@@ -286,13 +345,13 @@ NRB_DI void trav_start(LaneTrav &s, int *lm, int root, float tlimit) {
   s.tbest = tlimit;
 }
 
-template <bool HAS_SHAPES>
+template <bool HAS_SHAPES, int FMT>
 NRB_DI void trav_run(const SceneView &sc, LaneTrav &s, int *lm, bool any, int min_active) {
   int node = s.node, sp = s.sp;
   float tbest = s.tbest;
   while (node != kEmpty) {
     while ((unsigned)node < (unsigned)kEmpty) {
-      const NodeRec n = load_node(sc, node);
+      const NodeRec<FMT> n = load_node<FMT>(sc, node);
       float c0min, c0max, c1min, c1max;
       test_children(n, s.pre, tbest, c0min, c0max, c1min, c1max);
       bool h0 = c0max >= c0min, h1 = c1max >= c1min;
@@ -396,7 +455,7 @@ NRB_DI void nmap_closest(const SceneView &sc, V3 o, V3 d, Hit &hit);
 // ---------------------------------------------------------------------------------------------
 // K2 — closest hit of one ray (Scene::trace's best_first_search, src/scene.rs:164-166)
 // ---------------------------------------------------------------------------------------------
-template <bool HAS_SHAPES>
+template <bool HAS_SHAPES, int FMT>
 NRB_DI float4 closest_hit(const SceneView &sc, V3 o, V3 d) {
   Hit hit;
   hit.t = 3.402823466e+38f, hit.prim = kMiss, hit.u = hit.v = 0.0f;
@@ -410,7 +469,7 @@ NRB_DI float4 closest_hit(const SceneView &sc, V3 o, V3 d) {
       }
     }
   }
-  if (sc.root_all != kEmpty) traverse<HAS_SHAPES, false>(sc, sc.root_all, o, d, hit.t, hit);
+  if (sc.root_all != kEmpty) traverse<HAS_SHAPES, false, FMT>(sc, sc.root_all, o, d, hit.t, hit);
   if (HAS_SHAPES && sc.n_nmap > 0) nmap_closest(sc, o, d, hit);
   return make_float4(hit.t, __uint_as_float(hit.prim), hit.u, hit.v);
 }
@@ -505,7 +564,7 @@ NRB_DI bool aabb_toi_solid(const float lo[3], const float hi[3], V3 o, V3 d, flo
 // Closest hit of one nmap node with its toi shifted; false if the node is missed.
 NRB_DI bool nmap_cast(const SceneView &sc, const Candidate &nm, V3 o, V3 d, Hit &h) {
   h.t = 3.402823466e+38f, h.prim = kMiss, h.u = h.v = 0.0f;
-  if (!traverse<true, false>(sc, nm.root, o, d, 3.402823466e+38f, h)) return false;
+  if (!traverse<true, false, 0>(sc, nm.root, o, d, 3.402823466e+38f, h)) return false;
   Surface sf;
   reconstruct<true>(sc, o, d, h.prim, h.u, h.v, sf);
   if (sf.has_uv) {
@@ -563,12 +622,12 @@ NRB_DI bool nmap_shadow(const SceneView &sc, V3 o, V3 d, float tmax, V3 &filter)
 // Opaque-certain geometry lives under root_opaque (any-hit is exact for it); every node that can be
 // transparent has its own sub-root and is resolved by its own closest hit.
 // ---------------------------------------------------------------------------------------------
-template <bool HAS_SHAPES>
+template <bool HAS_SHAPES, int FMT>
 NRB_DI bool shadow_candidate(const SceneView &sc, int root, int node_id, V3 o, V3 d, float tmax, V3 &filter) {
   Hit h;
   h.t = 0, h.prim = kMiss, h.u = h.v = 0;
   // closest hit of this node with toi <= tmax
-  if (!traverse<HAS_SHAPES, false>(sc, root, o, d, nextafterf(tmax, 3.402823466e+38f), h)) return false;
+  if (!traverse<HAS_SHAPES, false, FMT>(sc, root, o, d, nextafterf(tmax, 3.402823466e+38f), h)) return false;
   Surface s;
   reconstruct<HAS_SHAPES>(sc, o, d, h.prim, h.u, h.v, s);
   const NodeInfo ni = sc.node_info[node_id];
@@ -584,7 +643,7 @@ NRB_DI bool shadow_candidate(const SceneView &sc, int root, int node_id, V3 o, V
 
 // The transparent-candidate part of the shadow query: every candidate SceneNode whose box the segment
 // crosses is resolved by its own closest hit (filter or occlusion).
-template <bool HAS_SHAPES>
+template <bool HAS_SHAPES, int FMT>
 NRB_DI bool shadow_candidates(const SceneView &sc, V3 o, V3 d, float tmax, V3 &filter) {
   bool occluded = false;
   if (sc.n_candidates > 0) {
@@ -592,13 +651,13 @@ NRB_DI bool shadow_candidates(const SceneView &sc, V3 o, V3 d, float tmax, V3 &f
     for (int c = 0; c < sc.n_candidates && !occluded; ++c) {
       const Candidate cd = sc.candidates[c];
       if (!box_hit(pre, cd.lo, cd.hi, tmax)) continue;  // bv cost of the candidate's box
-      occluded = shadow_candidate<HAS_SHAPES>(sc, cd.root, cd.node, o, d, tmax, filter);
+      occluded = shadow_candidate<HAS_SHAPES, FMT>(sc, cd.root, cd.node, o, d, tmax, filter);
     }
   }
   return occluded;
 }
 
-template <bool HAS_SHAPES>
+template <bool HAS_SHAPES, int FMT>
 NRB_DI void shadow_query(const SceneView &sc, V3 o, V3 d, float tmax, uint32_t pix, V3 contrib, float4 *accum) {
   bool occluded = false;
   V3 filter = mk(1, 1, 1);
@@ -630,9 +689,9 @@ NRB_DI void shadow_query(const SceneView &sc, V3 o, V3 d, float tmax, uint32_t p
   }
   if (!occluded && sc.root_opaque != kEmpty) {
     Hit h;
-    occluded = traverse<HAS_SHAPES, true>(sc, sc.root_opaque, o, d, tmax, h);
+    occluded = traverse<HAS_SHAPES, true, FMT>(sc, sc.root_opaque, o, d, tmax, h);
   }
-  if (!occluded) occluded = shadow_candidates<HAS_SHAPES>(sc, o, d, tmax, filter);
+  if (!occluded) occluded = shadow_candidates<HAS_SHAPES, FMT>(sc, o, d, tmax, filter);
   if (HAS_SHAPES && !occluded && sc.n_nmap > 0) occluded = nmap_shadow(sc, o, d, tmax, filter);
   if (!occluded) accum_add(accum, pix, cmul(contrib, filter));
 }
@@ -723,7 +782,7 @@ NRB_DI bool shadow_planes(const SceneView &sc, const ShadowQueue &sq, uint32_t i
   return false;
 }
 
-template <bool HAS_SHAPES>
+template <bool HAS_SHAPES, int FMT>
 NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *accum, WaveCounters *wc_shadow, int min_active,
                          bool reverse, uint32_t small_queue, RayPool *pool, int *lm) {
   const uint32_t count = min(wc_shadow->n_shadow, sq.capacity);
@@ -749,13 +808,13 @@ NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *acc
       continue;
     }
     if (active) {
-      trav_run<HAS_SHAPES>(sc, s, lm, cand < 0, min_active);
+      trav_run<HAS_SHAPES, FMT>(sc, s, lm, cand < 0, min_active);
       if (s.node == kEmpty) active = shadow_advance<HAS_SHAPES>(sc, sq, idx, s, lm, cand, false, reverse, accum);
     }
   }
 }
 
-template <bool HAS_SHAPES, bool PRIMARY>
+template <bool HAS_SHAPES, bool PRIMARY, int FMT>
 NRB_DI void drain_closest(const SceneView &sc, const FrameParams &fp, const RayQueue &q, float4 *hits,
                           WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, int min_active, uint32_t small_queue,
                           RayPool *pool, int *lm) {
@@ -804,7 +863,7 @@ NRB_DI void drain_closest(const SceneView &sc, const FrameParams &fp, const RayQ
       continue;
     }
     if (active) {
-      trav_run<HAS_SHAPES>(sc, s, lm, false, min_active);
+      trav_run<HAS_SHAPES, FMT>(sc, s, lm, false, min_active);
       if (s.node == kEmpty) {
         const uint32_t prim = (uint32_t)lm[kLmPrim];
         const bool hit = prim != kMiss;
@@ -816,7 +875,7 @@ NRB_DI void drain_closest(const SceneView &sc, const FrameParams &fp, const RayQ
   }
 }
 
-template <bool HAS_SHAPES, bool PRIMARY>
+template <bool HAS_SHAPES, bool PRIMARY, int FMT>
 __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 6 : kTraceMinBlocks)
     trace_kernel(SceneView sc, FrameParams fp, RayQueue q, float4 *hits, WaveCounters *wc_closest, uint32_t slot_lo,
                  uint32_t n_slots, ShadowQueue sq, float4 *accum, WaveCounters *wc_shadow, TraceOpts opts) {
@@ -827,10 +886,10 @@ __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 6 : kTraceMinBlocks)
   for (int phase = 0; phase < 2; ++phase) {
     if ((phase == 0) == closest_first) {
       if (wc_closest)
-        drain_closest<HAS_SHAPES, PRIMARY>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, opts.min_active_closest, opts.small_queue, pool, lm);
+        drain_closest<HAS_SHAPES, PRIMARY, FMT>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, opts.min_active_closest, opts.small_queue, pool, lm);
     } else {
       if (wc_shadow)
-        drain_shadow<HAS_SHAPES>(sc, sq, accum, wc_shadow, opts.min_active_shadow, opts.reverse_shadow != 0, opts.small_queue, pool, lm);
+        drain_shadow<HAS_SHAPES, FMT>(sc, sq, accum, wc_shadow, opts.min_active_shadow, opts.reverse_shadow != 0, opts.small_queue, pool, lm);
     }
   }
 }
@@ -852,7 +911,7 @@ __global__ void __launch_bounds__(kTraceBlock, 3)
       const uint32_t i = base + lane;
       if (i < count) {
         const float4 a = sq.a[i], b = sq.b[i], c = sq.c[i];
-        shadow_query<true>(sc, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), a.w, __float_as_uint(b.w), mk(c.x, c.y, c.z), accum);
+        shadow_query<true, 0>(sc, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), a.w, __float_as_uint(b.w), mk(c.x, c.y, c.z), accum);
       }
     }
   }
@@ -874,7 +933,7 @@ __global__ void __launch_bounds__(kTraceBlock, 3)
           const float4 a = q.a[i], b = q.b[i];
           o = mk(a.x, a.y, a.z), d = mk(a.w, b.x, b.y);
         }
-        hits[i] = valid ? closest_hit<true>(sc, o, d) : make_float4(0.0f, __uint_as_float(kSkip), 0.0f, 0.0f);
+        hits[i] = valid ? closest_hit<true, 0>(sc, o, d) : make_float4(0.0f, __uint_as_float(kSkip), 0.0f, 0.0f);
       }
     }
   }
@@ -1011,7 +1070,7 @@ NRB_DI void light_sample(const SceneView &sc, const FrameParams &fp, const RaySt
 
 // Writes the ray's shadow_samples light samples into slots [sbase, sbase + shadow_samples).
 // TRACE_ON_OVERFLOW (tail kernel): a sample that does not fit the queue is traced on the spot.
-template <bool HAS_SHAPES, bool TRACE_ON_OVERFLOW>
+template <bool HAS_SHAPES, bool TRACE_ON_OVERFLOW, int FMT>
 NRB_DI void emit_shadow_rays(const SceneView &sc, const FrameParams &fp, const RayState &r, const Shaded &s,
                              const ShadowQueue &sq, uint32_t sbase, Counters *ctr, float4 *accum) {
   uint32_t k_out = 0;
@@ -1029,7 +1088,7 @@ NRB_DI void emit_shadow_rays(const SceneView &sc, const FrameParams &fp, const R
         sq.b[si] = make_float4(ldir.x, ldir.y, ldir.z, __uint_as_float(s.pix));
         sq.c[si] = make_float4(c.x, c.y, c.z, 0.0f);
       } else if (TRACE_ON_OVERFLOW) {
-        shadow_query<HAS_SHAPES>(sc, so, ldir, dist, s.pix, c, accum);
+        shadow_query<HAS_SHAPES, FMT>(sc, so, ldir, dist, s.pix, c, accum);
       } else {
         ctr->overflow = 1u;
       }
@@ -1165,7 +1224,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
     const uint32_t sbase = sm.base[0] + __shfl_sync(0xFFFFFFFFu, woff_sh, 0) + __popc(m_sh & lt_mask) * S;
     const uint32_t cbase = sm.base[1] + __shfl_sync(0xFFFFFFFFu, woff_ch, 0) + __popc(m_rl & lt_mask) + __popc(m_rr & lt_mask);
 
-    if (s.emit_sh) emit_shadow_rays<HAS_SHAPES, false>(sc, fp, r, s, sq, sbase, ctr, accum);
+    if (s.emit_sh) emit_shadow_rays<HAS_SHAPES, false, 0>(sc, fp, r, s, sq, sbase, ctr, accum);
     if (s.want_refl) {
       if (cbase < qout.capacity)
         store_ray(qout, cbase, reflect_ray(r, s));
@@ -1191,7 +1250,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shade_kernel(Sce
 // counter `wc_sh`) that already holds the last shade's untraced shadow rays; ONE launch traces them all afterwards; when a hit spawns both children the refraction ray is spilled to `qspill`
 // (processed by the next tail launch).
 // ---------------------------------------------------------------------------------------------
-template <bool HAS_SHAPES>
+template <bool HAS_SHAPES, int FMT>
 __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : kTailMinBlocks) tail_kernel(SceneView sc, FrameParams fp, RayQueue qin,
                                                                               WaveCounters *wc, RayQueue qspill,
                                                                               ShadowQueue sq, Counters *ctr,
@@ -1209,7 +1268,7 @@ __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : kTailMinBlocks) 
     if (i < count) {
       RayState r = load_ray(qin, i);
       while (true) {
-        float4 h = closest_hit<HAS_SHAPES>(sc, r.o, r.d);
+        float4 h = closest_hit<HAS_SHAPES, FMT>(sc, r.o, r.d);
         ++c_tail;
         Shaded s;
         shade_eval<HAS_SHAPES>(sc, fp, r, h, true, accum, s);
@@ -1222,7 +1281,7 @@ __global__ void __launch_bounds__(kTraceBlock, HAS_SHAPES ? 3 : kTailMinBlocks) 
           uint32_t sbase = 0;
           if (g.thread_rank() == 0) sbase = atomicAdd(&wc_sh->n_shadow, S * g.size());
           sbase = g.shfl(sbase, 0) + S * g.thread_rank();
-          emit_shadow_rays<HAS_SHAPES, true>(sc, fp, r, s, sq, sbase, ctr, accum);
+          emit_shadow_rays<HAS_SHAPES, true, FMT>(sc, fp, r, s, sq, sbase, ctr, accum);
         }
         if (s.want_refl && s.want_refr) {
           ++c_refl, ++c_refr;
@@ -1335,6 +1394,62 @@ __global__ void resolve_tiles_to_segments_kernel(const float4 *accum, FrameParam
   dst[2] = make_float4(c.z * inv_spp, d.x * inv_spp, d.y * inv_spp, d.z * inv_spp);
 }
 
+// RGB8 forms of the two fused exchanges ("resolve + RGB8 quantise fused into the gather"): the finished pixels
+// leave the GPU as Image::to_png would encode them — clamp(c * 255, 0, 255) truncated to u8 (src/image.rs:64-77) — so the
+// exchange moves 3 bytes per pixel instead of 12, over NVLink (tiles_to_image) or PCIe (tiles_to_segments + 2-D DMA).
+NRB_DI uint32_t quant8(float c) { return (uint32_t)fminf(fmaxf(c * 255.0f, 0.0f), 255.0f); }
+NRB_DI void quant_px4(const float4 *src, float inv_spp, uint32_t w[3]) {
+  uint32_t b[12];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 a = src[k];
+    b[3 * k] = quant8(a.x * inv_spp), b[3 * k + 1] = quant8(a.y * inv_spp), b[3 * k + 2] = quant8(a.z * inv_spp);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) w[k] = b[4 * k] | (b[4 * k + 1] << 8) | (b[4 * k + 2] << 16) | (b[4 * k + 3] << 24);
+}
+
+__global__ void resolve_tiles_to_image_rgb8_kernel(const float4 *accum, FrameParams fp, float inv_spp, uint8_t *out_rgb8) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread = four pixels of one tile row = 12 bytes
+  if (t >= fp.n_local_tiles * (NRB_TILE * NRB_TILE / 4u)) return;
+  const uint32_t lt = t / (NRB_TILE * NRB_TILE / 4u), r = t % (NRB_TILE * NRB_TILE / 4u);
+  const uint32_t row = r / (NRB_TILE / 4u), x4 = (r % (NRB_TILE / 4u)) * 4u;
+  const uint32_t tile = fp.tile_first + lt * fp.tile_stride;
+  const uint32_t ty = fdiv(tile, fp.div_tiles_x), tx = tile - ty * fp.tiles_x;
+  const uint32_t y = ty * NRB_TILE + row, x = tx * NRB_TILE + x4;
+  if (y >= fp.height || x >= fp.width) return;
+  const float4 *src = accum + (size_t)lt * (NRB_TILE * NRB_TILE) + row * NRB_TILE + x4;
+  uint8_t *dst = out_rgb8 + 3u * ((size_t)y * fp.width + x);
+  if (x + 3u < fp.width && (fp.width & 3u) == 0u) {
+    uint32_t w[3];
+    quant_px4(src, inv_spp, w);
+    uint32_t *d4 = reinterpret_cast<uint32_t *>(dst);  // 3 * (y * W + x) bytes: 4-byte aligned when W % 4 == 0 and x % 4 == 0
+    d4[0] = w[0], d4[1] = w[1], d4[2] = w[2];
+  } else {
+    for (uint32_t k = 0; k < 4u && x + k < fp.width; ++k) {
+      const float4 a = src[k];
+      dst[3 * k + 0] = (uint8_t)quant8(a.x * inv_spp), dst[3 * k + 1] = (uint8_t)quant8(a.y * inv_spp), dst[3 * k + 2] = (uint8_t)quant8(a.z * inv_spp);
+    }
+  }
+}
+
+__global__ void resolve_tiles_to_segments_rgb8_kernel(const float4 *accum, FrameParams fp, float inv_spp, uint32_t cols_per_rank, uint8_t *stage) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= fp.n_local_tiles * (NRB_TILE * NRB_TILE / 4u)) return;
+  const uint32_t lt = t / (NRB_TILE * NRB_TILE / 4u), r = t % (NRB_TILE * NRB_TILE / 4u);
+  const uint32_t row = r / (NRB_TILE / 4u), x4 = (r % (NRB_TILE / 4u)) * 4u;
+  const uint32_t tile = fp.tile_first + lt * fp.tile_stride;
+  const uint32_t ty = fdiv(tile, fp.div_tiles_x), tx = tile - ty * fp.tiles_x;
+  const uint32_t y = ty * NRB_TILE + row;
+  if (y >= fp.height) return;
+  const uint32_t k = fdiv(tx - fp.tile_first, fp.div_tile_stride);
+  const float4 *src = accum + (size_t)lt * (NRB_TILE * NRB_TILE) + row * NRB_TILE + x4;
+  uint32_t w[3];
+  quant_px4(src, inv_spp, w);
+  uint32_t *dst = reinterpret_cast<uint32_t *>(stage + ((size_t)(y * cols_per_rank + k) * NRB_TILE + x4) * 3u);  // 48-byte segments
+  dst[0] = w[0], dst[1] = w[1], dst[2] = w[2];
+}
+
 // K6 — packed tiles of n_ranks ranks (rank r owns tiles r, r+n_ranks, ...) -> row-major image
 __global__ void untile_kernel(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width,
                               uint32_t height, uint32_t tiles_x, float *out_rgb) {
@@ -1356,13 +1471,19 @@ void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, b
                   WaveCounters *wc_closest, uint32_t slot_lo, uint32_t n_slots, ShadowQueue sq, float4 *accum,
                   WaveCounters *wc_shadow, TraceOpts opts, int grid, cudaStream_t st) {
   if (!wc_closest && !wc_shadow) return;
-#define NRB_LAUNCH_TRACE(HS, PR)                                                                                       \
-  trace_kernel<HS, PR><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow, \
-                                                     opts)
-  if (has_shapes) {
-    if (primary) NRB_LAUNCH_TRACE(true, true); else NRB_LAUNCH_TRACE(true, false);
-  } else {
-    if (primary) NRB_LAUNCH_TRACE(false, true); else NRB_LAUNCH_TRACE(false, false);
+#define NRB_LAUNCH_TRACE(HS, PR, FM)                                                                                          \
+  trace_kernel<HS, PR, FM><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow, \
+                                                         opts)
+  const int sel = (has_shapes ? 4 : 0) | (primary ? 2 : 0) | (sc.node_format == 2 ? 1 : 0);
+  switch (sel) {
+    case 0: NRB_LAUNCH_TRACE(false, false, 0); break;
+    case 1: NRB_LAUNCH_TRACE(false, false, 2); break;
+    case 2: NRB_LAUNCH_TRACE(false, true, 0); break;
+    case 3: NRB_LAUNCH_TRACE(false, true, 2); break;
+    case 4: NRB_LAUNCH_TRACE(true, false, 0); break;
+    case 5: NRB_LAUNCH_TRACE(true, false, 2); break;
+    case 6: NRB_LAUNCH_TRACE(true, true, 0); break;
+    default: NRB_LAUNCH_TRACE(true, true, 2); break;
   }
 #undef NRB_LAUNCH_TRACE
 }
@@ -1397,10 +1518,14 @@ void launch_shade(const SceneView &sc, bool has_shapes, const FrameParams &fp, b
 void launch_tail(const SceneView &sc, bool has_shapes, const FrameParams &fp, RayQueue qin, WaveCounters *wc,
                  RayQueue qspill, ShadowQueue sq, Counters *ctr, float4 *accum, WaveCounters *wc_sh, int grid,
                  cudaStream_t st) {
-  if (has_shapes)
-    tail_kernel<true><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum, wc_sh);
-  else
-    tail_kernel<false><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum, wc_sh);
+  const bool f2 = sc.node_format == 2;
+  if (has_shapes) {
+    if (f2) tail_kernel<true, 2><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum, wc_sh);
+    else tail_kernel<true, 0><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum, wc_sh);
+  } else {
+    if (f2) tail_kernel<false, 2><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum, wc_sh);
+    else tail_kernel<false, 0><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum, wc_sh);
+  }
 }
 
 int shade_blocks_per_sm(bool has_shapes) {
@@ -1443,6 +1568,18 @@ void launch_resolve_tiles_to_segments(const float4 *accum, const FrameParams &fp
   resolve_tiles_to_segments_kernel<<<(n + 255) / 256, 256, 0, st>>>(accum, fp, 1.0f / (float)fp.spp, cols_per_rank, stage);
 }
 
+void launch_resolve_tiles_to_image_rgb8(const float4 *accum, const FrameParams &fp, uint8_t *out_rgb8, cudaStream_t st) {
+  const uint32_t n = fp.n_local_tiles * (NRB_TILE * NRB_TILE / 4u);
+  if (!n) return;
+  resolve_tiles_to_image_rgb8_kernel<<<(n + 255) / 256, 256, 0, st>>>(accum, fp, 1.0f / (float)fp.spp, out_rgb8);
+}
+
+void launch_resolve_tiles_to_segments_rgb8(const float4 *accum, const FrameParams &fp, uint32_t cols_per_rank, uint8_t *stage, cudaStream_t st) {
+  const uint32_t n = fp.n_local_tiles * (NRB_TILE * NRB_TILE / 4u);
+  if (!n) return;
+  resolve_tiles_to_segments_rgb8_kernel<<<(n + 255) / 256, 256, 0, st>>>(accum, fp, 1.0f / (float)fp.spp, cols_per_rank, stage);
+}
+
 void launch_untile(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width, uint32_t height,
                    float *out_rgb, cudaStream_t st) {
   uint32_t n = width * height;
@@ -1465,11 +1602,11 @@ void debug_visit_counters(unsigned long long out[4], bool reset) {
 int trace_blocks_per_sm(bool has_shapes) {
   int nb = 0, nb2 = 0;
   if (has_shapes) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<true, false>, kTraceBlock, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, trace_kernel<true, true>, kTraceBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<true, false, 0>, kTraceBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, trace_kernel<true, true, 0>, kTraceBlock, 0);
   } else {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<false, false>, kTraceBlock, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, trace_kernel<false, true>, kTraceBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<false, false, 0>, kTraceBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, trace_kernel<false, true, 0>, kTraceBlock, 0);
   }
   nb = nb < nb2 ? nb : nb2;
   return nb > 0 ? nb : 1;

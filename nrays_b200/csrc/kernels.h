@@ -11,9 +11,6 @@ constexpr int kTraceBlock = 128;
 #ifndef NRB_TRACE_MIN_BLOCKS
 #define NRB_TRACE_MIN_BLOCKS 9
 #endif
-#ifndef NRB_NODE_LOADS
-#define NRB_NODE_LOADS 1
-#endif
 #ifndef NRB_SMALL_QUEUE
 #define NRB_SMALL_QUEUE (3u << 20)
 #endif
@@ -21,9 +18,10 @@ constexpr unsigned kSmallQueue = NRB_SMALL_QUEUE;  // default TraceOpts.small_qu
 constexpr int kFetchPackets = NRB_FETCH_PACKETS;  // 32-ray packets a warp takes per cursor atomic
 constexpr int kTraceMinBlocks = NRB_TRACE_MIN_BLOCKS;  // resident CTAs / SM the trace kernel is compiled for
 #ifndef NRB_TAIL_MIN_BLOCKS
-#define NRB_TAIL_MIN_BLOCKS 4
+#define NRB_TAIL_MIN_BLOCKS 6
 #endif
-constexpr int kTailMinBlocks = NRB_TAIL_MIN_BLOCKS;  // resident CTAs / SM of the tail kernel (mesh-only scenes)
+constexpr int kTailMinBlocks = NRB_TAIL_MIN_BLOCKS;  // resident CTAs / SM of the tail kernel (mesh-only scenes): 6 -> 80 registers with ~200 B of
+                                                   // spills beats 4 (114 registers, no spills) by 2.5 % of the C3 frame: the chains are latency-bound
 constexpr int kShadeBlock = 128;
 #ifndef NRB_SHADE_MIN_BLOCKS
 #define NRB_SHADE_MIN_BLOCKS 6
@@ -56,6 +54,8 @@ void launch_resolve_rgb8(const float4 *accum, uint32_t n, uint32_t spp, uint8_t 
 void launch_patch_host_image(const float4 *accum, const float *early_rgb, uint32_t n, uint32_t spp, float *host_rgb, cudaStream_t st);
 void launch_resolve_tiles_to_image(const float4 *accum, const FrameParams &fp, float *out_rgb, cudaStream_t st);
 void launch_resolve_tiles_to_segments(const float4 *accum, const FrameParams &fp, uint32_t cols_per_rank, float *stage, cudaStream_t st);
+void launch_resolve_tiles_to_image_rgb8(const float4 *accum, const FrameParams &fp, uint8_t *out_rgb8, cudaStream_t st);
+void launch_resolve_tiles_to_segments_rgb8(const float4 *accum, const FrameParams &fp, uint32_t cols_per_rank, uint8_t *stage, cudaStream_t st);
 void launch_untile(const float *gathered, uint32_t n_ranks, uint32_t tiles_per_rank, uint32_t width, uint32_t height,
                    float *out_rgb, cudaStream_t st);
 int trace_blocks_per_sm(bool has_shapes);

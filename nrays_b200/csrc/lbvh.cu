@@ -264,4 +264,259 @@ cudaError_t lbvh_build(const Box *h_boxes, uint32_t n, std::vector<BvhNode> &nod
   return cudaSuccess;
 }
 
+
+// =====================================================================================================================
+// PLOC — parallel locally-ordered clustering (Meister & Bittner, "Parallel Locally-Ordered Clustering for Bounding
+// Volume Hierarchy Construction", TVCG 2018).  Bottom-up agglomerative build on the Morton-sorted triangles: every
+// cluster looks r positions to the left and right for the neighbour whose merged box has the smallest surface area;
+// mutual nearest neighbours merge into a new node; the cluster array is compacted (one scan) and the loop repeats until one
+// cluster is left (~log_1.6 n rounds).  Unlike the radix tree of the LBVH — whose topology is dictated by Morton
+// prefixes — every merge is chosen by the SAH's own measure, so the tree traverses close to the host binned-SAH tree while
+// still building in a few milliseconds on the device.
+//
+// Nodes: ids [0, n) are the sorted triangles, [n, 2n-1) internal nodes in creation order (children always precede parents).
+// Post-pass: subtrees of <= 4 triangles collapse into one leaf; leaf positions come from a top-down offset pass run round
+// by round in reverse creation order (a parent's round is always later than its children's).
+// =====================================================================================================================
+namespace {
+
+__device__ __forceinline__ float union_half_area(const DBox &a, const DBox &b) {
+  float dx = fmaxf(a.hi[0], b.hi[0]) - fminf(a.lo[0], b.lo[0]);
+  float dy = fmaxf(a.hi[1], b.hi[1]) - fminf(a.lo[1], b.lo[1]);
+  float dz = fmaxf(a.hi[2], b.hi[2]) - fminf(a.lo[2], b.lo[2]);
+  return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void k_ploc_init(const DBox *boxes, const uint32_t *vals, int n, DBox *cbox, int *cid, DBox *node_box, int *node_count,
+                            int *node_height) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  DBox b = boxes[vals[i]];
+  cbox[i] = b, cid[i] = i;
+  node_box[i] = b, node_count[i] = 1, node_height[i] = 0;
+}
+
+// nearest neighbour within +-r positions by merged surface area; ties go to the smaller index (deterministic)
+__global__ void k_ploc_nn(const DBox *cbox, int m, int r, int *nn) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const DBox me = cbox[i];
+  float best = 3.402823466e+38f;
+  int bj = -1;
+  const int lo = max(0, i - r), hi = min(m - 1, i + r);
+  for (int j = lo; j <= hi; ++j) {
+    if (j == i) continue;
+    float a = union_half_area(me, cbox[j]);
+    if (a < best) best = a, bj = j;
+  }
+  nn[i] = bj;
+}
+
+// keys for the compaction scan: low word = cluster survives (1) or is absorbed by its partner (0); high word = cluster is
+// the LEFT member of a merging pair, i.e. creates a node
+__global__ void k_ploc_flags(const int *nn, int m, unsigned long long *key) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int j = nn[i];
+  const bool mutual = j >= 0 && nn[j] == i;
+  const unsigned long long keep = (mutual && j < i) ? 0ull : 1ull;
+  const unsigned long long make = (mutual && i < j) ? 1ull : 0ull;
+  key[i] = keep | (make << 32);
+}
+
+__global__ void k_ploc_apply(const DBox *cbox, const int *cid, const int *nn, const unsigned long long *key,
+                             const unsigned long long *scan, int m, int node_base, DBox *cbox_out, int *cid_out, DBox *node_box,
+                             int *node_left, int *node_right, int *node_count, int *node_height) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const unsigned long long k = key[i];
+  if (!(k & 1ull)) return;  // absorbed
+  const unsigned long long sc = scan[i];
+  const int pos = (int)(uint32_t)sc;
+  if (k >> 32) {
+    const int j = nn[i];
+    const int nid = node_base + (int)(uint32_t)(sc >> 32);
+    const DBox a = cbox[i], b = cbox[j];
+    DBox u;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) u.lo[q] = fminf(a.lo[q], b.lo[q]), u.hi[q] = fmaxf(a.hi[q], b.hi[q]);
+    const int l = cid[i], rr = cid[j];
+    const int cnt = node_count[l] + node_count[rr];
+    node_box[nid] = u, node_left[nid] = l, node_right[nid] = rr, node_count[nid] = cnt;
+    node_height[nid] = cnt <= kMaxLeafTris ? 0 : 1 + max(node_height[l], node_height[rr]);
+    cbox_out[pos] = u, cid_out[pos] = nid;
+  } else {
+    cbox_out[pos] = cbox[i], cid_out[pos] = cid[i];
+  }
+}
+
+__global__ void k_ploc_emit_flag(const int *node_count, int n, int n_internal, int *emit) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_internal) return;
+  emit[i] = node_count[n + i] > kMaxLeafTris ? 1 : 0;
+}
+
+// top-down leaf offsets for the internal nodes [first, last) of one round (parents of later rounds are done)
+__global__ void k_ploc_offsets(int n, int first, int last, const int *node_left, const int *node_right, const int *node_count,
+                               int *node_offset, const uint32_t *vals, uint32_t *order_out) {
+  int t = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= last) return;
+  const int off = node_offset[t];
+  const int l = node_left[t], r = node_right[t];
+  const int cl = node_count[l];
+  if (l < n) order_out[off] = vals[l]; else node_offset[l] = off;
+  if (r < n) order_out[off + cl] = vals[r]; else node_offset[r] = off + cl;
+}
+
+__device__ __forceinline__ int ploc_child_code(int c, int n, int pos, const int *node_count, const int *new_index) {
+  if (c < n) return make_leaf((uint32_t)pos, 1, false);
+  const int cnt = node_count[c];
+  if (cnt <= kMaxLeafTris) return make_leaf((uint32_t)pos, (uint32_t)cnt, false);
+  return new_index[c - n];
+}
+
+__global__ void k_ploc_emit(int n, int n_internal, const int *node_left, const int *node_right, const int *node_count,
+                            const int *node_offset, const DBox *node_box, const int *emit, const int *new_index, BvhNode *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_internal || !emit[i]) return;
+  const int t = n + i;
+  const int l = node_left[t], r = node_right[t];
+  const DBox a = node_box[l], b = node_box[r];
+  const int off = node_offset[t];
+  BvhNode nd;
+  nd.n0 = make_float4(a.lo[0], a.hi[0], a.lo[1], a.hi[1]);
+  nd.n1 = make_float4(b.lo[0], b.hi[0], b.lo[1], b.hi[1]);
+  nd.n2 = make_float4(a.lo[2], a.hi[2], b.lo[2], b.hi[2]);
+  nd.n3 = make_int4(ploc_child_code(l, n, off, node_count, new_index), ploc_child_code(r, n, off + node_count[l], node_count, new_index), 0, 0);
+  out[new_index[i]] = nd;
+}
+
+}  // namespace
+
+cudaError_t ploc_build(const Box *h_boxes, uint32_t n, int radius, std::vector<BvhNode> &nodes_out, std::vector<uint32_t> &order_out,
+                       int *root_code, Box *root_box, int *depth, float *gpu_ms) {
+  nodes_out.clear();
+  order_out.resize(n);
+  Box rb;
+  rb.reset();
+  for (uint32_t i = 0; i < n; ++i) rb.grow(h_boxes[i]);
+  *root_box = rb;
+  *depth = 0;
+  if (gpu_ms) *gpu_ms = 0.0f;
+  if (n <= (uint32_t)kMaxLeafTris) {
+    for (uint32_t i = 0; i < n; ++i) order_out[i] = i;
+    *root_code = make_leaf(0, n, false);
+    return cudaSuccess;
+  }
+  radius = radius < 1 ? 1 : (radius > 64 ? 64 : radius);
+  Scratch sc;
+  DBox *d_boxes, *d_cbox[2], *d_node_box;
+  unsigned long long *d_keys, *d_keys2, *d_flag, *d_scan;
+  uint32_t *d_vals, *d_vals2, *d_order;
+  int *d_cid[2], *d_nn, *d_left, *d_right, *d_count, *d_height, *d_offset, *d_emit, *d_new;
+  const size_t n_nodes = 2 * (size_t)n;
+  LB_CU(sc.alloc(&d_boxes, n));
+  LB_CU(sc.alloc(&d_cbox[0], n));
+  LB_CU(sc.alloc(&d_cbox[1], n));
+  LB_CU(sc.alloc(&d_node_box, n_nodes));
+  LB_CU(sc.alloc(&d_keys, n));
+  LB_CU(sc.alloc(&d_keys2, n));
+  LB_CU(sc.alloc(&d_flag, n));
+  LB_CU(sc.alloc(&d_scan, n));
+  LB_CU(sc.alloc(&d_vals, n));
+  LB_CU(sc.alloc(&d_vals2, n));
+  LB_CU(sc.alloc(&d_order, n));
+  LB_CU(sc.alloc(&d_cid[0], n));
+  LB_CU(sc.alloc(&d_cid[1], n));
+  LB_CU(sc.alloc(&d_nn, n));
+  LB_CU(sc.alloc(&d_left, n_nodes));
+  LB_CU(sc.alloc(&d_right, n_nodes));
+  LB_CU(sc.alloc(&d_count, n_nodes));
+  LB_CU(sc.alloc(&d_height, n_nodes));
+  LB_CU(sc.alloc(&d_offset, n_nodes));
+  LB_CU(sc.alloc(&d_emit, n));
+  LB_CU(sc.alloc(&d_new, n));
+  size_t scan_bytes = 0, sort_bytes = 0, scan2_bytes = 0;
+  LB_CU(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flag, d_scan, (int)n));
+  LB_CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63));
+  LB_CU(cub::DeviceScan::ExclusiveSum(nullptr, scan2_bytes, d_emit, d_new, (int)n));
+  char *d_tmp;
+  LB_CU(sc.alloc(&d_tmp, std::max(std::max(scan_bytes, sort_bytes), scan2_bytes)));
+  unsigned long long *h_last = nullptr;  // pinned: (scan, key) of the last cluster of the round
+  LB_CU(cudaHostAlloc((void **)&h_last, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+  struct Unpin {
+    void *p;
+    ~Unpin() { cudaFreeHost(p); }
+  } unpin{h_last};
+
+  LB_CU(cudaMemcpy(d_boxes, h_boxes, sizeof(DBox) * n, cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1;
+  LB_CU(cudaEventCreate(&e0));
+  LB_CU(cudaEventCreate(&e1));
+  LB_CU(cudaEventRecord(e0));
+  DBox scene;
+  std::memcpy(&scene, &rb, sizeof(scene));
+  const int T = 256;
+  k_morton<<<(n + T - 1) / T, T>>>(d_boxes, n, scene, d_keys, d_vals);
+  LB_CU(cub::DeviceRadixSort::SortPairs(d_tmp, sort_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63));
+  k_ploc_init<<<(n + T - 1) / T, T>>>(d_boxes, d_vals2, (int)n, d_cbox[0], d_cid[0], d_node_box, d_count, d_height);
+
+  std::vector<int> round_first;  // first internal node id of every round (+ end)
+  int m = (int)n, node_base = (int)n, cur = 0;
+  for (int round = 0; m > 1; ++round) {
+    if (round > 4096) return cudaErrorUnknown;  // cannot happen: every round merges at least the globally closest pair
+    round_first.push_back(node_base);
+    k_ploc_nn<<<(m + T - 1) / T, T>>>(d_cbox[cur], m, radius, d_nn);
+    k_ploc_flags<<<(m + T - 1) / T, T>>>(d_nn, m, d_flag);
+    LB_CU(cub::DeviceScan::ExclusiveSum(d_tmp, scan_bytes, d_flag, d_scan, m));
+    k_ploc_apply<<<(m + T - 1) / T, T>>>(d_cbox[cur], d_cid[cur], d_nn, d_flag, d_scan, m, node_base, d_cbox[1 - cur], d_cid[1 - cur],
+                                         d_node_box, d_left, d_right, d_count, d_height);
+    LB_CU(cudaMemcpyAsync(&h_last[0], d_scan + (m - 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    LB_CU(cudaMemcpyAsync(&h_last[1], d_flag + (m - 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    LB_CU(cudaStreamSynchronize(0));
+    const unsigned long long tot = h_last[0] + h_last[1];
+    const int kept = (int)(uint32_t)tot, made = (int)(uint32_t)(tot >> 32);
+    if (made <= 0 || kept != m - made) return cudaErrorUnknown;
+    m = kept, node_base += made, cur = 1 - cur;
+  }
+  round_first.push_back(node_base);
+  const int n_internal = node_base - (int)n;  // == n - 1
+  int root = 0, h_height = 0;
+  LB_CU(cudaMemcpy(&root, d_cid[cur], sizeof(int), cudaMemcpyDeviceToHost));
+  LB_CU(cudaMemcpy(&h_height, d_height + root, sizeof(int), cudaMemcpyDeviceToHost));
+  // leaf positions, top-down round by round
+  {
+    const int zero = 0;
+    LB_CU(cudaMemcpy(d_offset + root, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    for (int g = (int)round_first.size() - 2; g >= 0; --g) {
+      const int first = round_first[g], last = round_first[g + 1];
+      if (last > first)
+        k_ploc_offsets<<<(last - first + T - 1) / T, T>>>((int)n, first, last, d_left, d_right, d_count, d_offset, d_vals2, d_order);
+    }
+  }
+  k_ploc_emit_flag<<<(n_internal + T - 1) / T, T>>>(d_count, (int)n, n_internal, d_emit);
+  LB_CU(cub::DeviceScan::ExclusiveSum(d_tmp, scan2_bytes, d_emit, d_new, n_internal));
+  int last_new = 0, last_emit = 0;
+  LB_CU(cudaMemcpy(&last_new, d_new + (n_internal - 1), sizeof(int), cudaMemcpyDeviceToHost));
+  LB_CU(cudaMemcpy(&last_emit, d_emit + (n_internal - 1), sizeof(int), cudaMemcpyDeviceToHost));
+  const int n_out = last_new + last_emit;
+  BvhNode *d_out;
+  LB_CU(sc.alloc(&d_out, (size_t)std::max(n_out, 1)));
+  k_ploc_emit<<<(n_internal + T - 1) / T, T>>>((int)n, n_internal, d_left, d_right, d_count, d_offset, d_node_box, d_emit, d_new, d_out);
+  int root_new = 0;
+  LB_CU(cudaMemcpy(&root_new, d_new + (root - (int)n), sizeof(int), cudaMemcpyDeviceToHost));
+  LB_CU(cudaEventRecord(e1));
+  LB_CU(cudaDeviceSynchronize());
+  LB_CU(cudaGetLastError());
+  if (gpu_ms) cudaEventElapsedTime(gpu_ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  nodes_out.resize(n_out);
+  LB_CU(cudaMemcpy(nodes_out.data(), d_out, sizeof(BvhNode) * n_out, cudaMemcpyDeviceToHost));
+  LB_CU(cudaMemcpy(order_out.data(), d_order, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+  *root_code = root_new;  // n > 4: the root holds more than 4 triangles and is emitted
+  *depth = h_height;
+  return cudaSuccess;
+}
+
 }  // namespace nrb

@@ -12,4 +12,9 @@ namespace nrb {
 cudaError_t lbvh_build(const Box *h_boxes, uint32_t n, std::vector<BvhNode> &nodes_out, std::vector<uint32_t> &order_out,
                        int *root_code, Box *root_box, int *depth, float *gpu_ms);
 
+// Same contract, PLOC build (parallel locally-ordered clustering, search radius `radius`): merges are chosen by merged
+// surface area instead of Morton prefixes, so the tree traverses close to the host SAH tree.
+cudaError_t ploc_build(const Box *h_boxes, uint32_t n, int radius, std::vector<BvhNode> &nodes_out, std::vector<uint32_t> &order_out,
+                       int *root_code, Box *root_box, int *depth, float *gpu_ms);
+
 }  // namespace nrb

@@ -203,6 +203,27 @@ def render_tiles_to_image(scene, cam, rank, world, image_ptr):
 
 
 
+def render_tiles_to_image_rgb8(scene, cam, rank, world, image_ptr):
+    """RGB8 form of render_tiles_to_image: W*H*3 BYTES at `image_ptr`, quantised like Image::to_png (src/image.rs:64-77)."""
+    from . import _lib
+
+    ts = A.NrbTileSet(rank, world)
+    stats = A.NrbStats()
+    ptr = image_ptr if isinstance(image_ptr, C.c_void_p) else C.c_void_p(int(image_ptr))
+    _lib.check(_lib.load().nrb_render_tiles_to_image_rgb8(scene.handle, C.byref(cam), C.byref(ts), ptr, C.byref(stats)))
+    return stats
+
+
+def render_tiles_to_host_rgb8(scene, cam, rank, world, host_addr):
+    """RGB8 form of render_tiles_to_host: the rank's tile columns as 48-byte segments, one strided 2-D DMA."""
+    from . import _lib
+
+    ts = A.NrbTileSet(rank, world)
+    stats = A.NrbStats()
+    _lib.check(_lib.load().nrb_render_tiles_to_host_rgb8(scene.handle, C.byref(cam), C.byref(ts), C.c_void_p(int(host_addr)), C.byref(stats)))
+    return stats
+
+
 # ---- end-to-end exchange: N ranks fill ONE shared pinned host image through their own PCIe links ------------------
 class SharedHostImage:
     """Row-major W*H*3 float image in POSIX shared memory, mapped by every rank of the node and registered with CUDA in

@@ -483,7 +483,7 @@ class Scene:
         self.background = tuple(float(x) for x in background)
         self.flat = FlatScene(self.nodes, self._lights, self.background)
         self.device = device
-        self.builder = builder  # "sah" (host binned SAH) or "lbvh" (device build); None: library default / env NRB_BUILDER
+        self.builder = builder  # "sah" (host binned SAH), "lbvh" or "ploc" (device builds); None: library default / env NRB_BUILDER
         self._handle = None
         if upload:
             self.upload()
@@ -498,7 +498,7 @@ class Scene:
         if self.builder is None:
             _lib.check(lib.nrb_scene_create_opts(C.byref(self.flat.desc), int(self.device), None, C.byref(h)))
         else:
-            opts = A.NrbBuildOptions(A.NRB_BUILDER_LBVH if self.builder == "lbvh" else A.NRB_BUILDER_SAH)
+            opts = A.NrbBuildOptions({"lbvh": A.NRB_BUILDER_LBVH, "ploc": A.NRB_BUILDER_PLOC}.get(self.builder, A.NRB_BUILDER_SAH))
             _lib.check(lib.nrb_scene_create_opts(C.byref(self.flat.desc), int(self.device), C.byref(opts), C.byref(h)))
         self._handle = h
 

@@ -1,4 +1,5 @@
-"""SAH (host) vs LBVH (device) builders: build time and frame time on a BASELINE config."""
+"""SAH (host) vs LBVH / PLOC (device) builders: build time and frame time on a BASELINE config.
+NRB_PLOC_RADIUS selects the PLOC search radius (default 16); NRB_BUILD_TIMES=1 prints the host phases of Scene::new."""
 import ctypes as C
 import os
 import sys
@@ -16,7 +17,7 @@ for cfgname in sys.argv[1:] or ["C3", "C4"]:
     lights, nodes, cams = parse(cfg["text"](), cfg["resolver"]())
     w, h, spp = cfg["width"], cfg["height"], cfg["spp"]
     out = torch.empty(w * h * 3, dtype=torch.float32, device="cuda")
-    for builder in ("sah", "lbvh"):
+    for builder in (os.environ.get("EXP_BUILDERS", "sah,lbvh,ploc").split(",")):
         t0 = time.time()
         scene = Scene(nodes, lights, (1, 1, 1), builder=builder)
         wall = time.time() - t0

@@ -9,7 +9,7 @@ rm -f gpurun_out/parity_report.jsonl
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${T}_smi.txt 2>&1
 nproc >> gpurun_out/${T}_smi.txt
 if [ "$MODE" = "tests" ]; then
-  ( timeout 2400 python -m pytest tests -m gpu -q -x --durations=15 2>&1 | tail -60 ) > gpurun_out/${T}_pytest.log
+  ( timeout 2400 python -m pytest tests -m gpu -q --durations=15 2>&1 | tail -60 ) > gpurun_out/${T}_pytest.log
   cp gpurun_out/parity_report.jsonl gpurun_out/${T}_parity.jsonl 2>/dev/null
 fi
 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err

@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import fuzz_parity as FZ  # noqa: E402
 import oracle_lib as O  # noqa: E402
 from nrays_b200 import Scene, make_camera  # noqa: E402
-from util import TOL, _nbhd_min_max, edge_flip_report, look, render_both  # noqa: E402
+from util import TOL, _nbhd_min_max, edge_flip_report, look, render_both, unexplained_allowed  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -53,7 +53,7 @@ def test_fuzz_slice(gpu, seed, n_scenes):
         rep = edge_flip_report(img, ref, (w, h))
         tot_px += w * h
         tot_over += rep["over"]
-        if rep["unexplained"] == 0 and _counts_ok(st, ost):
+        if rep["unexplained"] <= unexplained_allowed(w * h) and _counts_ok(st, ost):
             continue
         # ---- prove it: precision-chaotic, or fail ------------------------------------------------------------
         sc = Scene(nodes, lights, (1.0, 1.0, 1.0), upload=False)
