@@ -8,7 +8,10 @@
 #include <cstring>
 #include <deque>
 #include <memory>
+#include <mutex>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/nrays_b200.h"
@@ -56,6 +59,33 @@ struct DevBuf {
   }
 };
 
+// Large POD host array WITHOUT value-initialisation (a std::vector zero-fills on one thread; these arrays are filled by
+// parallel loops right after allocation).
+template <class T>
+struct HostArray {
+  std::unique_ptr<T[]> p;
+  size_t n = 0;
+  void resize_uninit(size_t count) {
+    p.reset(count ? new T[count] : nullptr);
+    n = count;
+  }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T *data() { return p.get(); }
+  const T *data() const { return p.get(); }
+  T &operator[](size_t i) { return p[i]; }
+  const T &operator[](size_t i) const { return p[i]; }
+};
+
+template <class T>
+cudaError_t upload(DevBuf &b, const HostArray<T> &v) {
+  size_t n = std::max<size_t>(v.size() * sizeof(T), 16);
+  cudaError_t e = b.ensure(n);
+  if (e != cudaSuccess) return e;
+  if (!v.empty()) e = cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+
 template <class T>
 cudaError_t upload(DevBuf &b, const std::vector<T> &v) {
   size_t n = std::max<size_t>(v.size() * sizeof(T), 16);
@@ -63,6 +93,26 @@ cudaError_t upload(DevBuf &b, const std::vector<T> &v) {
   if (e != cudaSuccess) return e;
   if (!v.empty()) e = cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
   return e;
+}
+
+// Host-side data-parallel loop for the per-triangle phases of Scene::new (transform, gathers): contiguous chunks, one per
+// hardware thread (NRB_BVH_THREADS overrides); small ranges run inline.
+template <class F>
+void parallel_for(size_t n, F &&fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  if (const char *e = getenv("NRB_BVH_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+  if (n < 65536 || hw < 2) {
+    fn(0, n);
+    return;
+  }
+  const size_t chunk = (n + hw - 1) / hw;
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < hw; ++t) {
+    const size_t lo = (size_t)t * chunk, hi = std::min(n, lo + chunk);
+    if (lo >= hi) break;
+    pool.emplace_back([&fn, lo, hi]() { fn(lo, hi); });
+  }
+  for (auto &t : pool) t.join();
 }
 
 size_t env_size(const char *name, size_t dflt) {
@@ -139,7 +189,12 @@ int relayout_bfs(std::vector<BvhNode> &nodes, int &root_all, int &root_opaque, s
   };
   add_root(root_all);
   for (auto &c : nmaps) add_root(c.root);  // depth-shift nodes keep their own sub-trees outside root_all
-  for (size_t head = 0; head < order.size(); ++head) {
+  // Level order for the TOP of the tree (what every ray touches: kept contiguous, a few MB), builder order below it: the
+  // builders emit a parent before its subtrees (depth-first), which keeps a deep path's nodes close together and costs one
+  // linear sweep here instead of a random-access BFS over millions of nodes.  NRB_RELAYOUT_TOP=0 restores the full BFS.
+  const size_t top_cap = env_size("NRB_RELAYOUT_TOP", 1u << 16);
+  size_t head = 0;
+  for (; head < order.size() && (top_cap == 0 || order.size() < top_cap); ++head) {
     const BvhNode &n = nodes[order[head]];
     int ch[2] = {n.n3.x, n.n3.y};
     for (int c : ch)
@@ -148,13 +203,24 @@ int relayout_bfs(std::vector<BvhNode> &nodes, int &root_all, int &root_opaque, s
         order.push_back(c);
       }
   }
-  std::vector<BvhNode> out(order.size());
-  for (size_t i = 0; i < order.size(); ++i) {
-    BvhNode n = nodes[order[i]];
-    if (n.n3.x >= 0) n.n3.x = remap[n.n3.x];
-    if (n.n3.y >= 0) n.n3.y = remap[n.n3.y];
-    out[i] = n;
+  if (head < order.size() || order.size() < nodes.size()) {
+    // everything not placed yet that is reachable: sweep in builder order (children of placed nodes are reachable by construction;
+    // unreachable nodes do not exist — every builder node hangs off root_all or an nmap root)
+    for (size_t i = 0; i < nodes.size(); ++i)
+      if (remap[i] < 0) {
+        remap[i] = (int)order.size();
+        order.push_back((int)i);
+      }
   }
+  std::vector<BvhNode> out(order.size());
+  parallel_for(order.size(), [&](size_t lo_i, size_t hi_i) {
+    for (size_t i = lo_i; i < hi_i; ++i) {
+      BvhNode n = nodes[order[i]];
+      if (n.n3.x >= 0) n.n3.x = remap[n.n3.x];
+      if (n.n3.y >= 0) n.n3.y = remap[n.n3.y];
+      out[i] = n;
+    }
+  });
   auto fix = [&](int &c) {
     if (c >= 0 && c != kEmpty) c = remap[c];
   };
@@ -169,8 +235,8 @@ int relayout_bfs(std::vector<BvhNode> &nodes, int &root_all, int &root_opaque, s
 // Host-side result of Scene::new: validated tables + BVH, ready to upload.
 struct HostScene {
   std::vector<BvhNode> nodes;
-  std::vector<Tri> tris;
-  std::vector<TriUV> tri_uvs;
+  HostArray<Tri> tris;
+  HostArray<TriUV> tri_uvs;
   std::vector<Shape> shapes;
   std::vector<NodeInfo> node_info;
   std::vector<Material> materials;
@@ -311,55 +377,73 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
   if (total_tris >= (1ull << 28)) return fail(NRB_ERR_INVALID_ARG, "too many triangles (>= 2^28)");
 
   // ---- triangles to world space (f64 transform, then f32) -------------------------------------
-  std::vector<Tri> tris_in(total_tris);
-  std::vector<TriUV> uvs_in(total_tris);
-  std::vector<Box> tri_box(total_tris);
+  // uninitialised on purpose: a std::vector would zero 280 MB on ONE thread before the parallel transform touches it
+  std::unique_ptr<Tri[]> tris_in(new Tri[total_tris]);
+  std::unique_ptr<TriUV[]> uvs_in(new TriUV[total_tris]);
+  std::unique_ptr<Box[]> tri_box(new Box[total_tris]);
   std::vector<uint64_t> node_tri_begin(d.n_nodes, 0);
   Box scene_box;
   scene_box.reset();
   {
     uint64_t t_out = 0;
+    std::atomic<int> bad_node(-1);
     for (uint32_t i = 0; i < d.n_nodes; ++i) {
       const NrbNodeDesc &n = d.nodes[i];
       if (n.shape != NRB_SHAPE_TRIMESH) continue;
       node_tri_begin[i] = t_out;
-      for (uint64_t t = 0; t < n.tri_count; ++t, ++t_out) {
-        double w[3][3];
-        TriUV uv{};
-        for (int k = 0; k < 3; ++k) {
-          uint64_t vi = (uint64_t)d.indices[n.first_index + 3 * t + k] + n.vertex_base;
-          if (vi >= d.n_vertices) return fail(NRB_ERR_INVALID_ARG, "node " + std::to_string(i) + ": vertex index out of range");
-          const float *p = d.positions + 3 * vi;
-          for (int r = 0; r < 3; ++r)
-            w[k][r] = n.rot[3 * r] * (double)p[0] + n.rot[3 * r + 1] * (double)p[1] + n.rot[3 * r + 2] * (double)p[2] + n.trans[r];
-          float uu = d.uvs ? d.uvs[2 * vi] : 0.0f, vv = d.uvs ? d.uvs[2 * vi + 1] : 0.0f;
-          if (k == 0) uv.u0 = uu, uv.v0 = vv;
-          if (k == 1) uv.u1 = uu, uv.v1 = vv;
-          if (k == 2) uv.u2 = uu, uv.v2 = vv;
+      const uint64_t base = t_out;
+      std::vector<Box> part_box;  // per-chunk scene boxes, merged below
+      std::mutex part_mu;
+      parallel_for((size_t)n.tri_count, [&](size_t lo_t, size_t hi_t) {
+        Box local;
+        local.reset();
+        for (uint64_t t = lo_t; t < hi_t; ++t) {
+          double w[3][3];
+          TriUV uv{};
+          for (int k = 0; k < 3; ++k) {
+            uint64_t vi = (uint64_t)d.indices[n.first_index + 3 * t + k] + n.vertex_base;
+            if (vi >= d.n_vertices) {
+              bad_node.store((int)i);
+              return;
+            }
+            const float *p = d.positions + 3 * vi;
+            for (int r = 0; r < 3; ++r)
+              w[k][r] = n.rot[3 * r] * (double)p[0] + n.rot[3 * r + 1] * (double)p[1] + n.rot[3 * r + 2] * (double)p[2] + n.trans[r];
+            float uu = d.uvs ? d.uvs[2 * vi] : 0.0f, vv = d.uvs ? d.uvs[2 * vi + 1] : 0.0f;
+            if (k == 0) uv.u0 = uu, uv.v0 = vv;
+            if (k == 1) uv.u1 = uu, uv.v1 = vv;
+            if (k == 2) uv.u2 = uu, uv.v2 = vv;
+          }
+          Tri tr;
+          tr.t0 = make_float4((float)w[0][0], (float)w[0][1], (float)w[0][2], 0.0f);
+          int node_id = (int)i;
+          std::memcpy(&tr.t0.w, &node_id, 4);
+          tr.t1 = make_float4((float)(w[1][0] - w[0][0]), (float)(w[1][1] - w[0][1]), (float)(w[1][2] - w[0][2]), 0.0f);
+          int material_id = (int)n.material;  // copy of NodeInfo.material: shade fetches the material without waiting for NodeInfo
+          std::memcpy(&tr.t1.w, &material_id, 4);
+          tr.t2 = make_float4((float)(w[2][0] - w[0][0]), (float)(w[2][1] - w[0][1]), (float)(w[2][2] - w[0][2]), 0.0f);
+          tris_in[base + t] = tr;
+          uvs_in[base + t] = uv;
+          Box b;
+          b.reset();
+          float v0[3] = {tr.t0.x, tr.t0.y, tr.t0.z};
+          float v1[3] = {tr.t0.x + tr.t1.x, tr.t0.y + tr.t1.y, tr.t0.z + tr.t1.z};
+          float v2[3] = {tr.t0.x + tr.t2.x, tr.t0.y + tr.t2.y, tr.t0.z + tr.t2.z};
+          b.grow(v0), b.grow(v1), b.grow(v2);
+          for (int k = 0; k < 3; ++k) {
+            float wk[3] = {(float)w[k][0], (float)w[k][1], (float)w[k][2]};
+            b.grow(wk);
+          }
+          tri_box[base + t] = b;
+          local.grow(b);
         }
-        Tri tr;
-        tr.t0 = make_float4((float)w[0][0], (float)w[0][1], (float)w[0][2], 0.0f);
-        int node_id = (int)i;
-        std::memcpy(&tr.t0.w, &node_id, 4);
-        tr.t1 = make_float4((float)(w[1][0] - w[0][0]), (float)(w[1][1] - w[0][1]), (float)(w[1][2] - w[0][2]), 0.0f);
-        int material_id = (int)n.material;  // copy of NodeInfo.material: shade fetches the material without waiting for NodeInfo
-        std::memcpy(&tr.t1.w, &material_id, 4);
-        tr.t2 = make_float4((float)(w[2][0] - w[0][0]), (float)(w[2][1] - w[0][1]), (float)(w[2][2] - w[0][2]), 0.0f);
-        tris_in[t_out] = tr;
-        uvs_in[t_out] = uv;
-        Box b;
-        b.reset();
-        float v0[3] = {tr.t0.x, tr.t0.y, tr.t0.z};
-        float v1[3] = {tr.t0.x + tr.t1.x, tr.t0.y + tr.t1.y, tr.t0.z + tr.t1.z};
-        float v2[3] = {tr.t0.x + tr.t2.x, tr.t0.y + tr.t2.y, tr.t0.z + tr.t2.z};
-        b.grow(v0), b.grow(v1), b.grow(v2);
-        for (int k = 0; k < 3; ++k) {
-          float wk[3] = {(float)w[k][0], (float)w[k][1], (float)w[k][2]};
-          b.grow(wk);
-        }
-        tri_box[t_out] = b;
-        scene_box.grow(b);
-      }
+        std::lock_guard<std::mutex> g(part_mu);
+        part_box.push_back(local);
+      });
+      if (bad_node.load() >= 0) return fail(NRB_ERR_INVALID_ARG, "node " + std::to_string(bad_node.load()) + ": vertex index out of range");
+      for (const Box &b : part_box)
+        if (b.valid()) scene_box.grow(b);
+      t_out += n.tri_count;
     }
   }
   pt.lap("triangles to world space");
@@ -401,7 +485,9 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
   float extent = 0.0f;
   if (scene_box.valid())
     for (int k = 0; k < 3; ++k) extent = std::max(extent, scene_box.hi[k] - scene_box.lo[k]);
-  for (auto &b : tri_box) pad_box(b, extent);
+  parallel_for((size_t)total_tris, [&](size_t lo_t, size_t hi_t) {
+    for (size_t k = lo_t; k < hi_t; ++k) pad_box(tri_box[k], extent);
+  });
   for (size_t si = 0; si < shapes.size(); ++si)
     if (shape_box[si].valid()) pad_box(shape_box[si], extent);
 
@@ -414,7 +500,9 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
   auto build_set = [&](std::vector<BuildItem> &items, Box *rb, int *code) -> int {
     if (builder == NRB_BUILDER_LBVH || builder == NRB_BUILDER_PLOC) {
       std::vector<Box> boxes(items.size());
-      for (size_t k = 0; k < items.size(); ++k) boxes[k] = items[k].box;
+      parallel_for(items.size(), [&](size_t lo_t, size_t hi_t) {
+        for (size_t k = lo_t; k < hi_t; ++k) boxes[k] = items[k].box;
+      });
       std::vector<BvhNode> sub;
       std::vector<uint32_t> order;
       int depth = 0, root = kEmpty;
@@ -431,12 +519,19 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
         uint32_t lc = (uint32_t)~c;
         return ~(int)((((lc >> 3) + tri_off) << 3) | (lc & 7u));
       };
-      for (BvhNode nd : sub) {
-        nd.n3.x = shift(nd.n3.x);
-        nd.n3.y = shift(nd.n3.y);
-        bb.nodes.push_back(nd);
-      }
-      for (uint32_t pos : order) bb.tri_order.push_back((uint32_t)items[pos].payload);
+      bb.nodes.resize((size_t)node_off + sub.size());
+      parallel_for(sub.size(), [&](size_t lo_t, size_t hi_t) {
+        for (size_t k = lo_t; k < hi_t; ++k) {
+          BvhNode nd = sub[k];
+          nd.n3.x = shift(nd.n3.x);
+          nd.n3.y = shift(nd.n3.y);
+          bb.nodes[(size_t)node_off + k] = nd;
+        }
+      });
+      bb.tri_order.resize((size_t)tri_off + order.size());
+      parallel_for(order.size(), [&](size_t lo_t, size_t hi_t) {
+        for (size_t k = lo_t; k < hi_t; ++k) bb.tri_order[(size_t)tri_off + k] = (uint32_t)items[order[k]].payload;
+      });
       *code = shift(root);
       bb.max_depth_seen = std::max(bb.max_depth_seen, depth + 1);
       return NRB_OK;
@@ -449,7 +544,12 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
     for (uint32_t i = 0; i < d.n_nodes; ++i) {
       const NrbNodeDesc &n = d.nodes[i];
       if (n.shape != NRB_SHAPE_TRIMESH || is_cand[i] || is_nmap[i]) continue;
-      for (uint64_t t = 0; t < n.tri_count; ++t) items.push_back(BuildItem{tri_box[node_tri_begin[i] + t], (int)(node_tri_begin[i] + t)});
+      const size_t at = items.size();
+      items.resize(at + n.tri_count);
+      const uint64_t b0 = node_tri_begin[i];
+      parallel_for((size_t)n.tri_count, [&](size_t lo_t, size_t hi_t) {
+        for (size_t t = lo_t; t < hi_t; ++t) items[at + t] = BuildItem{tri_box[b0 + t], (int)(b0 + t)};
+      });
     }
     if (!items.empty()) {
       Box rb;
@@ -553,9 +653,11 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
   pt.lap("level-order relayout");
 
   // leaf-ordered triangle arrays
-  H.tris.resize(bb.tri_order.size());
-  H.tri_uvs.resize(bb.tri_order.size());
-  for (size_t k = 0; k < bb.tri_order.size(); ++k) H.tris[k] = tris_in[bb.tri_order[k]], H.tri_uvs[k] = uvs_in[bb.tri_order[k]];
+  H.tris.resize_uninit(bb.tri_order.size());
+  H.tri_uvs.resize_uninit(bb.tri_order.size());
+  parallel_for(bb.tri_order.size(), [&](size_t lo_t, size_t hi_t) {
+    for (size_t k = lo_t; k < hi_t; ++k) H.tris[k] = tris_in[bb.tri_order[k]], H.tri_uvs[k] = uvs_in[bb.tri_order[k]];
+  });
   pt.lap("leaf-ordered triangle arrays");
   H.nodes.swap(bb.nodes);
   H.shapes.swap(shapes);

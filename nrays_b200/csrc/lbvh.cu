@@ -11,6 +11,10 @@
 // Tree shape never changes render results, only traversal cost: the LBVH builds ~100x faster
 // than the host binned-SAH build and traverses slower, so SAH stays the default (NrbBuildOptions.builder).
 // The sort is cub::DeviceRadixSort (a library call, outside the render hot path).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 
 #include "lbvh.h"
@@ -160,6 +164,18 @@ __global__ void k_emit(const DBox *boxes, const uint32_t *vals, int n, const int
   out[new_index[i]] = nd;
 }
 
+struct BuildClock {  // NRB_BUILD_TIMES=1: host-side phases of the device builders on stderr
+  bool on = getenv("NRB_BUILD_TIMES") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char *what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[nrb] build:   device builder: %-22s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 struct Scratch {
   std::vector<void *> ptrs;
   ~Scratch() {
@@ -287,13 +303,20 @@ __device__ __forceinline__ float union_half_area(const DBox &a, const DBox &b) {
   return dx * dy + dy * dz + dz * dx;
 }
 
+__device__ __forceinline__ float half_area(const DBox &a) {
+  float dx = a.hi[0] - a.lo[0], dy = a.hi[1] - a.lo[1], dz = a.hi[2] - a.lo[2];
+  return dx * dy + dy * dz + dz * dx;
+}
+
+constexpr float kPlocCostNode = 1.2f;  // cost of one two-box node visit relative to one triangle test (as the host SAH builder)
+
 __global__ void k_ploc_init(const DBox *boxes, const uint32_t *vals, int n, DBox *cbox, int *cid, DBox *node_box, int *node_count,
-                            int *node_height) {
+                            int *node_height, float *node_cost) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   DBox b = boxes[vals[i]];
   cbox[i] = b, cid[i] = i;
-  node_box[i] = b, node_count[i] = 1, node_height[i] = 0;
+  node_box[i] = b, node_count[i] = 1, node_height[i] = 0, node_cost[i] = half_area(b);
 }
 
 // nearest neighbour within +-r positions by merged surface area; ties go to the smaller index (deterministic)
@@ -326,7 +349,7 @@ __global__ void k_ploc_flags(const int *nn, int m, unsigned long long *key) {
 
 __global__ void k_ploc_apply(const DBox *cbox, const int *cid, const int *nn, const unsigned long long *key,
                              const unsigned long long *scan, int m, int node_base, DBox *cbox_out, int *cid_out, DBox *node_box,
-                             int *node_left, int *node_right, int *node_count, int *node_height) {
+                             int *node_left, int *node_right, int *node_count, int *node_height, float *node_cost, int *node_leaf) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const unsigned long long k = key[i];
@@ -343,39 +366,47 @@ __global__ void k_ploc_apply(const DBox *cbox, const int *cid, const int *nn, co
     const int l = cid[i], rr = cid[j];
     const int cnt = node_count[l] + node_count[rr];
     node_box[nid] = u, node_left[nid] = l, node_right[nid] = rr, node_count[nid] = cnt;
-    node_height[nid] = cnt <= kMaxLeafTris ? 0 : 1 + max(node_height[l], node_height[rr]);
+    // SAH decision, bottom-up: a subtree of <= 4 triangles becomes ONE leaf only if testing all its triangles is cheaper than
+    // descending (the host builder decides the same way, bvh_build.cpp)
+    const float area = half_area(u);
+    const float split = kPlocCostNode * area + node_cost[l] + node_cost[rr];
+    const float as_leaf = (float)cnt * area;
+    const bool leaf = cnt <= kMaxLeafTris && as_leaf <= split;
+    node_cost[nid] = leaf ? as_leaf : split;
+    node_leaf[nid] = leaf ? 1 : 0;
+    node_height[nid] = leaf ? 0 : 1 + max(node_height[l], node_height[rr]);
     cbox_out[pos] = u, cid_out[pos] = nid;
   } else {
     cbox_out[pos] = cbox[i], cid_out[pos] = cid[i];
   }
 }
 
-__global__ void k_ploc_emit_flag(const int *node_count, int n, int n_internal, int *emit) {
+__global__ void k_ploc_emit_flag(const int *node_leaf, const int *node_inside, int n, int n_internal, int *emit) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_internal) return;
-  emit[i] = node_count[n + i] > kMaxLeafTris ? 1 : 0;
+  emit[i] = (!node_leaf[n + i] && !node_inside[n + i]) ? 1 : 0;
 }
 
 // top-down leaf offsets for the internal nodes [first, last) of one round (parents of later rounds are done)
 __global__ void k_ploc_offsets(int n, int first, int last, const int *node_left, const int *node_right, const int *node_count,
-                               int *node_offset, const uint32_t *vals, uint32_t *order_out) {
+                               const int *node_leaf, int *node_offset, int *node_inside, const uint32_t *vals, uint32_t *order_out) {
   int t = first + blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= last) return;
   const int off = node_offset[t];
   const int l = node_left[t], r = node_right[t];
   const int cl = node_count[l];
-  if (l < n) order_out[off] = vals[l]; else node_offset[l] = off;
-  if (r < n) order_out[off + cl] = vals[r]; else node_offset[r] = off + cl;
+  const int inside = node_inside[t] | node_leaf[t];  // everything below a leaf-subtree root is part of that leaf
+  if (l < n) order_out[off] = vals[l]; else node_offset[l] = off, node_inside[l] = inside;
+  if (r < n) order_out[off + cl] = vals[r]; else node_offset[r] = off + cl, node_inside[r] = inside;
 }
 
-__device__ __forceinline__ int ploc_child_code(int c, int n, int pos, const int *node_count, const int *new_index) {
+__device__ __forceinline__ int ploc_child_code(int c, int n, int pos, const int *node_count, const int *node_leaf, const int *new_index) {
   if (c < n) return make_leaf((uint32_t)pos, 1, false);
-  const int cnt = node_count[c];
-  if (cnt <= kMaxLeafTris) return make_leaf((uint32_t)pos, (uint32_t)cnt, false);
+  if (node_leaf[c]) return make_leaf((uint32_t)pos, (uint32_t)node_count[c], false);
   return new_index[c - n];
 }
 
-__global__ void k_ploc_emit(int n, int n_internal, const int *node_left, const int *node_right, const int *node_count,
+__global__ void k_ploc_emit(int n, int n_internal, const int *node_left, const int *node_right, const int *node_count, const int *node_leaf,
                             const int *node_offset, const DBox *node_box, const int *emit, const int *new_index, BvhNode *out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_internal || !emit[i]) return;
@@ -387,7 +418,8 @@ __global__ void k_ploc_emit(int n, int n_internal, const int *node_left, const i
   nd.n0 = make_float4(a.lo[0], a.hi[0], a.lo[1], a.hi[1]);
   nd.n1 = make_float4(b.lo[0], b.hi[0], b.lo[1], b.hi[1]);
   nd.n2 = make_float4(a.lo[2], a.hi[2], b.lo[2], b.hi[2]);
-  nd.n3 = make_int4(ploc_child_code(l, n, off, node_count, new_index), ploc_child_code(r, n, off + node_count[l], node_count, new_index), 0, 0);
+  nd.n3 = make_int4(ploc_child_code(l, n, off, node_count, node_leaf, new_index),
+                    ploc_child_code(r, n, off + node_count[l], node_count, node_leaf, new_index), 0, 0);
   out[new_index[i]] = nd;
 }
 
@@ -409,11 +441,13 @@ cudaError_t ploc_build(const Box *h_boxes, uint32_t n, int radius, std::vector<B
     return cudaSuccess;
   }
   radius = radius < 1 ? 1 : (radius > 64 ? 64 : radius);
+  BuildClock clk;
   Scratch sc;
   DBox *d_boxes, *d_cbox[2], *d_node_box;
   unsigned long long *d_keys, *d_keys2, *d_flag, *d_scan;
   uint32_t *d_vals, *d_vals2, *d_order;
-  int *d_cid[2], *d_nn, *d_left, *d_right, *d_count, *d_height, *d_offset, *d_emit, *d_new;
+  int *d_cid[2], *d_nn, *d_left, *d_right, *d_count, *d_height, *d_offset, *d_emit, *d_new, *d_leaf, *d_inside;
+  float *d_cost;
   const size_t n_nodes = 2 * (size_t)n;
   LB_CU(sc.alloc(&d_boxes, n));
   LB_CU(sc.alloc(&d_cbox[0], n));
@@ -434,8 +468,13 @@ cudaError_t ploc_build(const Box *h_boxes, uint32_t n, int radius, std::vector<B
   LB_CU(sc.alloc(&d_count, n_nodes));
   LB_CU(sc.alloc(&d_height, n_nodes));
   LB_CU(sc.alloc(&d_offset, n_nodes));
+  LB_CU(sc.alloc(&d_leaf, n_nodes));
+  LB_CU(sc.alloc(&d_inside, n_nodes));
+  LB_CU(sc.alloc(&d_cost, n_nodes));
   LB_CU(sc.alloc(&d_emit, n));
   LB_CU(sc.alloc(&d_new, n));
+  LB_CU(cudaMemset(d_leaf, 0, sizeof(int) * n_nodes));
+  LB_CU(cudaMemset(d_inside, 0, sizeof(int) * n_nodes));
   size_t scan_bytes = 0, sort_bytes = 0, scan2_bytes = 0;
   LB_CU(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flag, d_scan, (int)n));
   LB_CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63));
@@ -449,7 +488,9 @@ cudaError_t ploc_build(const Box *h_boxes, uint32_t n, int radius, std::vector<B
     ~Unpin() { cudaFreeHost(p); }
   } unpin{h_last};
 
+  clk.lap("cudaMalloc");
   LB_CU(cudaMemcpy(d_boxes, h_boxes, sizeof(DBox) * n, cudaMemcpyHostToDevice));
+  clk.lap("boxes to device");
   cudaEvent_t e0, e1;
   LB_CU(cudaEventCreate(&e0));
   LB_CU(cudaEventCreate(&e1));
@@ -459,7 +500,8 @@ cudaError_t ploc_build(const Box *h_boxes, uint32_t n, int radius, std::vector<B
   const int T = 256;
   k_morton<<<(n + T - 1) / T, T>>>(d_boxes, n, scene, d_keys, d_vals);
   LB_CU(cub::DeviceRadixSort::SortPairs(d_tmp, sort_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63));
-  k_ploc_init<<<(n + T - 1) / T, T>>>(d_boxes, d_vals2, (int)n, d_cbox[0], d_cid[0], d_node_box, d_count, d_height);
+  clk.lap("morton + sort");
+  k_ploc_init<<<(n + T - 1) / T, T>>>(d_boxes, d_vals2, (int)n, d_cbox[0], d_cid[0], d_node_box, d_count, d_height, d_cost);
 
   std::vector<int> round_first;  // first internal node id of every round (+ end)
   int m = (int)n, node_base = (int)n, cur = 0;
@@ -470,7 +512,7 @@ cudaError_t ploc_build(const Box *h_boxes, uint32_t n, int radius, std::vector<B
     k_ploc_flags<<<(m + T - 1) / T, T>>>(d_nn, m, d_flag);
     LB_CU(cub::DeviceScan::ExclusiveSum(d_tmp, scan_bytes, d_flag, d_scan, m));
     k_ploc_apply<<<(m + T - 1) / T, T>>>(d_cbox[cur], d_cid[cur], d_nn, d_flag, d_scan, m, node_base, d_cbox[1 - cur], d_cid[1 - cur],
-                                         d_node_box, d_left, d_right, d_count, d_height);
+                                         d_node_box, d_left, d_right, d_count, d_height, d_cost, d_leaf);
     LB_CU(cudaMemcpyAsync(&h_last[0], d_scan + (m - 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     LB_CU(cudaMemcpyAsync(&h_last[1], d_flag + (m - 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     LB_CU(cudaStreamSynchronize(0));
@@ -480,6 +522,7 @@ cudaError_t ploc_build(const Box *h_boxes, uint32_t n, int radius, std::vector<B
     m = kept, node_base += made, cur = 1 - cur;
   }
   round_first.push_back(node_base);
+  clk.lap("clustering rounds");
   const int n_internal = node_base - (int)n;  // == n - 1
   int root = 0, h_height = 0;
   LB_CU(cudaMemcpy(&root, d_cid[cur], sizeof(int), cudaMemcpyDeviceToHost));
@@ -491,10 +534,10 @@ cudaError_t ploc_build(const Box *h_boxes, uint32_t n, int radius, std::vector<B
     for (int g = (int)round_first.size() - 2; g >= 0; --g) {
       const int first = round_first[g], last = round_first[g + 1];
       if (last > first)
-        k_ploc_offsets<<<(last - first + T - 1) / T, T>>>((int)n, first, last, d_left, d_right, d_count, d_offset, d_vals2, d_order);
+        k_ploc_offsets<<<(last - first + T - 1) / T, T>>>((int)n, first, last, d_left, d_right, d_count, d_leaf, d_offset, d_inside, d_vals2, d_order);
     }
   }
-  k_ploc_emit_flag<<<(n_internal + T - 1) / T, T>>>(d_count, (int)n, n_internal, d_emit);
+  k_ploc_emit_flag<<<(n_internal + T - 1) / T, T>>>(d_leaf, d_inside, (int)n, n_internal, d_emit);
   LB_CU(cub::DeviceScan::ExclusiveSum(d_tmp, scan2_bytes, d_emit, d_new, n_internal));
   int last_new = 0, last_emit = 0;
   LB_CU(cudaMemcpy(&last_new, d_new + (n_internal - 1), sizeof(int), cudaMemcpyDeviceToHost));
@@ -502,7 +545,7 @@ cudaError_t ploc_build(const Box *h_boxes, uint32_t n, int radius, std::vector<B
   const int n_out = last_new + last_emit;
   BvhNode *d_out;
   LB_CU(sc.alloc(&d_out, (size_t)std::max(n_out, 1)));
-  k_ploc_emit<<<(n_internal + T - 1) / T, T>>>((int)n, n_internal, d_left, d_right, d_count, d_offset, d_node_box, d_emit, d_new, d_out);
+  k_ploc_emit<<<(n_internal + T - 1) / T, T>>>((int)n, n_internal, d_left, d_right, d_count, d_leaf, d_offset, d_node_box, d_emit, d_new, d_out);
   int root_new = 0;
   LB_CU(cudaMemcpy(&root_new, d_new + (root - (int)n), sizeof(int), cudaMemcpyDeviceToHost));
   LB_CU(cudaEventRecord(e1));
@@ -511,10 +554,12 @@ cudaError_t ploc_build(const Box *h_boxes, uint32_t n, int radius, std::vector<B
   if (gpu_ms) cudaEventElapsedTime(gpu_ms, e0, e1);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  clk.lap("offsets + emit");
   nodes_out.resize(n_out);
   LB_CU(cudaMemcpy(nodes_out.data(), d_out, sizeof(BvhNode) * n_out, cudaMemcpyDeviceToHost));
   LB_CU(cudaMemcpy(order_out.data(), d_order, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
-  *root_code = root_new;  // n > 4: the root holds more than 4 triangles and is emitted
+  clk.lap("tree to host");
+  *root_code = root_new;  // n > 4: the root holds more than 4 triangles, cannot be a leaf and is emitted
   *depth = h_height;
   return cudaSuccess;
 }
