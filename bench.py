@@ -359,7 +359,7 @@ def measure_config(ctx, cfg_id, steps, warmup):
         peak, peak_src = peaks()
         s0 = stats_dev[0][0]
         n_steps = len(stats_dev)
-        geom_bytes = s0["bvh_nodes"] * 64 + s0["triangles"] * 48
+        geom_bytes = s0["scene_bytes"]   # nodes + leaf-ordered triangles (+ uvs, texels) as resident on the device
         # ---- (1) the dominant kernel alone: trace_kernel on THIS rank (NrbStats.ms_trace / launches_trace exclude the tail
         # kernel).  Compulsory HBM bytes: a closest-hit ray reads 32 B of queue entry and writes a 16 B hit record (wave 0
         # generates its rays on chip: 16 B only); a shadow ray reads 48 B and issues one 16 B RED; the geometry (64 B nodes

@@ -188,6 +188,8 @@ int relayout_bfs(std::vector<BvhNode> &nodes, int &root_all, int &root_opaque, s
     }
   };
   add_root(root_all);
+  add_root(root_opaque);                   // separate from root_all when the closest-hit tree is unified (flatten_scene)
+  for (auto &c : cands) add_root(c.root);
   for (auto &c : nmaps) add_root(c.root);  // depth-shift nodes keep their own sub-trees outside root_all
   // Level order for the TOP of the tree (what every ray touches: kept contiguous, a few MB), builder order below it: the
   // builders emit a parent before its subtrees (depth-first), which keeps a deep path's nodes close together and costs one
@@ -248,6 +250,8 @@ struct HostScene {
   int root_all = kEmpty, root_opaque = kEmpty;
   int shadow_samples = 0;
   bool any_refl = false, any_refr = false;
+  uint64_t n_source_tris = 0;  // triangles of the scene (H.tris holds one entry per LEAF reference: twice that with a unified tree)
+  bool unified = false;  // root_all is a separate tree over all triangles (the shadow structure hangs off root_opaque + candidates)
   uint32_t refl_chain_max = 0;
   int depth_tri = 0, depth_mid = 0, depth_top = 0;
   float gpu_build_ms = 0.0f;  // device time of the LBVH kernels (NRB_BUILDER_LBVH)
@@ -638,12 +642,53 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
     depth_mid = bb.max_depth_seen;
     top_items.push_back(BuildItem{rb, root_opaque});
   }
-  if (!top_items.empty()) {
+  // ---- closest-hit entry (root_all) ------------------------------------------------------------------------------------
+  // Shadow queries need the per-SceneNode structure above (opaque tree + one sub-root per transparent candidate).  Closest-hit
+  // queries do not: when candidate MESHES exist, a separate tree over ALL triangles serves them.  Joining the candidates'
+  // sub-trees under a top node would make every ray walk several overlapping trees (foliage quads are spread through the
+  // whole atrium): the unified tree needs 15 % fewer node visits per primary ray on C3 (27.9 vs 33.0, scripts/bvh_sim.cpp)
+  // at the price of a second copy of the nodes and leaf-ordered triangles.  NRB_UNIFIED_TREE=0 restores the joined form.
+  bool any_cand_mesh = false;
+  for (uint32_t i = 0; i < d.n_nodes; ++i)
+    any_cand_mesh = any_cand_mesh || (d.nodes[i].shape == NRB_SHAPE_TRIMESH && is_cand[i] && !is_nmap[i]);
+  int depth_all = 0;
+  if (any_cand_mesh && env_size("NRB_UNIFIED_TREE", 1) != 0) {
+    std::vector<BuildItem> items;
+    for (uint32_t i = 0; i < d.n_nodes; ++i) {
+      const NrbNodeDesc &n = d.nodes[i];
+      if (n.shape != NRB_SHAPE_TRIMESH || is_nmap[i]) continue;
+      const size_t at = items.size();
+      items.resize(at + n.tri_count);
+      const uint64_t b0 = node_tri_begin[i];
+      parallel_for((size_t)n.tri_count, [&](size_t lo_t, size_t hi_t) {
+        for (size_t t = lo_t; t < hi_t; ++t) items[at + t] = BuildItem{tri_box[b0 + t], (int)(b0 + t)};
+      });
+    }
+    std::vector<BuildItem> all_items;
+    Box rb;
+    bb.max_depth_seen = 0;
+    int code = kEmpty;
+    int brc = build_set(items, &rb, &code);
+    if (brc) return brc;
+    depth_all = bb.max_depth_seen;
+    all_items.push_back(BuildItem{rb, code});
+    for (uint32_t i = 0; i < d.n_nodes; ++i) {
+      const NrbNodeDesc &n = d.nodes[i];
+      if (n.shape == NRB_SHAPE_TRIMESH || n.shape == NRB_SHAPE_PLANE || is_nmap[i]) continue;
+      const int si = shape_of_node[i];
+      all_items.push_back(BuildItem{shape_box[si], make_leaf((uint32_t)si, 1, true)});
+    }
+    bb.max_depth_seen = 0;
+    root_all = bb.build_payloads(all_items, &rb);
+    depth_top = bb.max_depth_seen;
+    H.unified = true;
+  } else if (!top_items.empty()) {
     Box rb;
     bb.max_depth_seen = 0;
     root_all = bb.build_payloads(top_items, &rb);
     depth_top = bb.max_depth_seen;
   }
+  if (H.unified && depth_all + depth_top + 4 > kStackSize) return fail(NRB_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
   // one stack slot per level at most (the far child of each two-hit node) + the sentinel
   if (depth_tri + depth_mid + depth_top + 4 > kStackSize)
     return fail(NRB_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
@@ -669,6 +714,7 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
   H.candidates.swap(candidates);
   H.nmaps.swap(nmaps);
   H.root_all = root_all, H.root_opaque = root_opaque;
+  H.n_source_tris = total_tris;
   H.shadow_samples = shadow_samples;
   H.any_refl = any_refl, H.any_refr = any_refr;
   H.depth_tri = depth_tri, H.depth_mid = depth_mid, H.depth_top = depth_top;
@@ -686,6 +732,10 @@ int check_bvh(const HostScene &H, std::string &why) {
   };
   std::vector<Item> stack;
   if (H.root_all != kEmpty) stack.push_back(Item{H.root_all, Box{}, false});
+  if (H.unified) {  // the shadow structure is a second set of trees over the same triangles
+    if (H.root_opaque != kEmpty) stack.push_back(Item{H.root_opaque, Box{}, false});
+    for (const Candidate &c : H.candidates) stack.push_back(Item{c.root, Box{}, false});
+  }
   for (const Candidate &nm : H.nmaps) stack.push_back(Item{nm.root, Box{}, false});
   auto inside = [](const Box &outer, const Box &inner) {
     for (int k = 0; k < 3; ++k)
@@ -898,7 +948,7 @@ int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
   S.child_factor = (H.any_refl ? 1 : 0) + (H.any_refr ? 1 : 0);
   S.refl_chain_max = H.refl_chain_max;
   S.n_bvh_nodes = H.nodes.size();
-  S.n_tris = H.tris.size();
+  S.n_tris = H.n_source_tris;
   S.node_bytes = 64;  // stride; format 2 reads 48 of them per visit
   S.scene_bytes = H.nodes.size() * S.node_bytes + H.tris.size() * (sizeof(Tri) + sizeof(TriUV)) +
                   H.shapes.size() * sizeof(Shape) + d.n_texels * 16;
@@ -1412,7 +1462,7 @@ int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOp
   rc = upload_scene(*desc, H, *S);
   if (rc) return rc;
   S->build_info.bvh_nodes = H.nodes.size();
-  S->build_info.triangles = H.tris.size();
+  S->build_info.triangles = H.n_source_tris;
   S->build_info.shapes = H.shapes.size();
   S->build_info.planes = H.planes.size();
   S->build_info.transparent_candidates = H.candidates.size();
@@ -1458,7 +1508,7 @@ int nrb_scene_validate(const NrbSceneDesc *desc, NrbBuildInfo *info) {
   if (info) {
     std::memset(info, 0, sizeof(*info));
     info->bvh_nodes = H.nodes.size();
-    info->triangles = H.tris.size();
+    info->triangles = H.n_source_tris;
     info->shapes = H.shapes.size();
     info->planes = H.planes.size();
     info->transparent_candidates = H.candidates.size();
