@@ -1502,6 +1502,9 @@ int nrb_scene_validate(const NrbSceneDesc *desc, NrbBuildInfo *info) {
       fwrite(hdr, sizeof(hdr), 1, f);
       fwrite(H.nodes.data(), sizeof(BvhNode), H.nodes.size(), f);
       fwrite(H.tris.data(), sizeof(Tri), H.tris.size(), f);
+      uint64_t nc = H.candidates.size();  // trailer: the shadow structure's transparent candidates
+      fwrite(&nc, sizeof(nc), 1, f);
+      fwrite(H.candidates.data(), sizeof(Candidate), H.candidates.size(), f);
       fclose(f);
     }
   }

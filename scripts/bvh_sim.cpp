@@ -28,6 +28,7 @@ static V3 norm(V3 a) { return a * (1.0f / std::sqrt(dot(a, a))); }
 static std::vector<Node> nodes;
 static std::vector<Tri> tris;
 static uint64_t n_visits, n_tests, n_rays;
+static bool g_no_shrink = false;
 
 static bool tri_hit(const Tri &T, V3 o, V3 d, float tlimit, bool inclusive, float &toi) {
   V3 v0{T.t0.x, T.t0.y, T.t0.z}, e1{T.t1.x, T.t1.y, T.t1.z}, e2{T.t2.x, T.t2.y, T.t2.z};
@@ -88,7 +89,7 @@ static bool traverse(int root, V3 o, V3 d, float tmax, bool any, float &tout) {
           ++n_tests;
           float toi;
           if (tri_hit(tris[first + k], o, d, tbest, any, toi)) {
-            tbest = toi;
+            if (!g_no_shrink) tbest = toi;
             found = true;
             if (any) { tout = toi; return true; }
           }
@@ -111,6 +112,15 @@ int main(int argc, char **argv) {
   tris.resize(hdr[1]);
   if (fread(nodes.data(), sizeof(Node), nodes.size(), f) != nodes.size()) return 1;
   if (fread(tris.data(), sizeof(Tri), tris.size(), f) != tris.size()) return 1;
+  struct Cand { float lo[3], hi[3]; int root, node; };
+  std::vector<Cand> cands;
+  {
+    uint64_t nc = 0;
+    if (fread(&nc, sizeof(nc), 1, f) == 1 && nc < 4096) {
+      cands.resize(nc);
+      if (fread(cands.data(), sizeof(Cand), nc, f) != nc) cands.clear();
+    }
+  }
   fclose(f);
   int root_all = (int)(uint32_t)hdr[2], root_opaque = (int)(uint32_t)hdr[3];
   V3 eye{(float)atof(argv[2]), (float)atof(argv[3]), (float)atof(argv[4])};
@@ -121,7 +131,7 @@ int main(int argc, char **argv) {
   if (argc >= 15) light = V3{(float)atof(argv[12]), (float)atof(argv[13]), (float)atof(argv[14])};
   V3 fw = norm(at - eye), rt = norm(cross(fw, V3{0, 1, 0})), up = cross(rt, fw);
   float th = std::tan(fovy / 2), aspect = (float)W / H;
-  uint64_t pv = 0, pt = 0, pr = 0, sv = 0, st = 0, sr = 0, hits = 0;
+  uint64_t pv = 0, pt = 0, pr = 0, sv = 0, st = 0, sr = 0, hits = 0, cv = 0, ct = 0, uv_ = 0, ut = 0;
   for (int y = 0; y < H; y += step)
     for (int x = 0; x < W; x += step) {
       float nx = ((float)x / W - 0.5f) * 2, ny = -((float)y / H - 0.5f) * 2;
@@ -141,9 +151,21 @@ int main(int argc, char **argv) {
           float ts;
           traverse(root_opaque != kEmpty ? root_opaque : root_all, p + l * 0.001f, l, len - 0.001f, true, ts);
           sv += n_visits, st += n_tests, sr += 1;
+          // the candidate phases of the shadow query: one closest-hit traversal per candidate sub-root
+          n_visits = n_tests = 0;
+          for (const Cand &c : cands) traverse(c.root, p + l * 0.001f, l, len - 0.001f, false, ts);
+          cv += n_visits, ct += n_tests;
+          // alternative: ONE pass over the unified tree that never shrinks its interval (every node overlapping the segment)
+          n_visits = n_tests = 0;
+          g_no_shrink = true;
+          traverse(root_all, p + l * 0.001f, l, len - 0.001f, false, ts);
+          g_no_shrink = false;
+          uv_ += n_visits, ut += n_tests;
         }
       }
     }
+  if (sr) printf("shadow candidates (%zu): %.2f visits %.2f tests per ray | unified no-shrink pass: %.2f visits %.2f tests\n", cands.size(),
+                 (double)cv / sr, (double)ct / sr, (double)uv_ / sr, (double)ut / sr);
   printf("nodes %zu tris %zu | primary: %.2f visits %.2f tests (%llu rays, %.1f%% hit) | shadow: %.2f visits %.2f tests (%llu rays)\n",
          nodes.size(), tris.size(), (double)pv / pr, (double)pt / pr, (unsigned long long)pr, 100.0 * hits / pr,
          sr ? (double)sv / sr : 0.0, sr ? (double)st / sr : 0.0, (unsigned long long)sr);
