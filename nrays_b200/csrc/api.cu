@@ -152,6 +152,9 @@ struct NrbScene {
   // tail changed follow as an ordered patch
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_early = nullptr, ev_copied = nullptr;
+  // wave ray counts travel to the host on their own stream: a 4-byte device->host copy in the render stream would sit between
+  // two dependent kernels for ~10 us (DMA set-up), once per wave
+  cudaStream_t count_stream = nullptr;
 
   ~NrbScene() {
     cudaSetDevice(device);
@@ -162,6 +165,7 @@ struct NrbScene {
     if (ev_end) cudaEventDestroy(ev_end);
     if (own_stream) cudaStreamDestroy(own_stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (count_stream) cudaStreamDestroy(count_stream);
     if (ev_early) cudaEventDestroy(ev_early);
     if (ev_copied) cudaEventDestroy(ev_copied);
   }
@@ -1099,6 +1103,8 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   const uint32_t small_queue = (uint32_t)env_size("NRB_SMALL_QUEUE", fine_geometry ? 0xFFFFFFFFu : kSmallQueue);
   uint64_t primary = 0;
 
+  if (!S.count_stream) CU(cudaStreamCreateWithFlags(&S.count_stream, cudaStreamNonBlocking));
+  cudaEvent_t last_count_ev = nullptr;
   const size_t wc_len = (size_t)fp.max_depth + 3;
   CU(S.d_wave.ensure(wc_len * sizeof(WaveCounters)));
   WaveCounters *wc = S.d_wave.as<WaveCounters>();
@@ -1116,6 +1122,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
       n0 += (uint64_t)wpx * hpx * fp.spp;
     }
     primary += n0;
+    if (last_count_ev) CU(cudaStreamWaitEvent(st, last_count_ev, 0));  // the side stream has read the previous batch's counters
     CU(cudaMemsetAsync(wc, 0, wc_len * sizeof(WaveCounters), st));  // the only counter reset of the batch
 
     // Pipelined waves.  Wave k >= 1 consumes queue k%2 holding n_k = wc[k].n_rays rays (written by the
@@ -1225,10 +1232,14 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
         S.h_wave_counts[wave_base] = (uint32_t)n0;
         count_ev.push_back(nullptr);
       } else {
-        CU(cudaMemcpyAsync(&S.h_wave_counts[wave_base + k], &wc[k].n_rays, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        cudaEvent_t ev = get_event(S, ev_used);
-        CU(cudaEventRecord(ev, st));
+        // wc[k].n_rays is final once the shade of wave k-1 (already enqueued) has run: read it back on the side stream
+        cudaEvent_t ready = get_event(S, ev_used), ev = get_event(S, ev_used);
+        CU(cudaEventRecord(ready, st));
+        CU(cudaStreamWaitEvent(S.count_stream, ready, 0));
+        CU(cudaMemcpyAsync(&S.h_wave_counts[wave_base + k], &wc[k].n_rays, sizeof(uint32_t), cudaMemcpyDeviceToHost, S.count_stream));
+        CU(cudaEventRecord(ev, S.count_stream));
         count_ev.push_back(ev);
+        last_count_ev = ev;
       }
       ++wave_counts_used;
       const uint64_t emitters = (k == 0) ? n0 : bound;  // rays that can spawn children / shadow rays
@@ -1337,6 +1348,7 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   CU(cudaEventRecord(S.ev_end, st));
   CU(cudaMemcpyAsync(S.h_counters, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  CU(cudaStreamSynchronize(S.count_stream));
   CU(cudaGetLastError());
   for (size_t i = 0; i < wave_counts_used; ++i) waves += S.h_wave_counts[i] ? 1u : 0u;
   if (dump) {
