@@ -115,6 +115,13 @@ void parallel_for(size_t n, F &&fn) {
   for (auto &t : pool) t.join();
 }
 
+// Sample slots per batch and shadow-queue entries per wave.  Every batch pays its own launches and the tail of each persistent
+// kernel (its slowest warps), so frames larger than one batch want big batches: C5 (132.7 M slots) 30.3 ms at 8 Mi slots,
+// 28.9 at 16 Mi, 28.4 at 32 Mi, 28.2 at 64 Mi; C4 (16.6 M slots) 8.27 -> 7.90 ms once it is one batch.  32 Mi slots cost
+// 0.5 GB of hit records + 1.5 GB of shadow queue + up to 1.5 GB per ray queue — small change on a 180 GB part.
+constexpr size_t kBatchSlots = 32u << 20;
+constexpr size_t kShadowCap = 32u << 20;
+
 size_t env_size(const char *name, size_t dflt) {
   const char *s = getenv(name);
   if (!s || !*s) return dflt;
@@ -1065,8 +1072,8 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   const bool dump = getenv("NRB_DUMP_WAVES") != nullptr;
 
   {
-    uint64_t n_batches = (fp.n_local_tiles + std::max<uint64_t>(1, env_size("NRB_BATCH_SLOTS", 8u << 20) / (NRB_TILE * NRB_TILE * fp.spp)) - 1) /
-                         std::max<uint64_t>(1, env_size("NRB_BATCH_SLOTS", 8u << 20) / (NRB_TILE * NRB_TILE * fp.spp));
+    uint64_t n_batches = (fp.n_local_tiles + std::max<uint64_t>(1, env_size("NRB_BATCH_SLOTS", kBatchSlots) / (NRB_TILE * NRB_TILE * fp.spp)) - 1) /
+                         std::max<uint64_t>(1, env_size("NRB_BATCH_SLOTS", kBatchSlots) / (NRB_TILE * NRB_TILE * fp.spp));
     size_t need = (size_t)(n_batches + 1) * ((size_t)fp.max_depth + 2);
     if (need > S.h_wave_cap) {
       CU(cudaStreamSynchronize(st));
@@ -1082,9 +1089,9 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
 
   const uint32_t per_tile = NRB_TILE * NRB_TILE * fp.spp;
   const uint64_t total_slots = (uint64_t)fp.n_local_tiles * per_tile;
-  const uint64_t batch_slots_req = env_size("NRB_BATCH_SLOTS", 8u << 20);
+  const uint64_t batch_slots_req = env_size("NRB_BATCH_SLOTS", kBatchSlots);
   const uint32_t tiles_per_batch = (uint32_t)std::max<uint64_t>(1, batch_slots_req / per_tile);
-  const uint64_t shadow_cap_req = env_size("NRB_SHADOW_CAP", 16u << 20);
+  const uint64_t shadow_cap_req = env_size("NRB_SHADOW_CAP", kShadowCap);
   const uint64_t mem_ceiling = env_size("NRB_QUEUE_BYTES", 64ull << 30);
   const uint32_t S_total = (uint32_t)S.view.shadow_samples;
   const uint64_t tail_threshold = env_size("NRB_TAIL_RAYS", 4u << 20);

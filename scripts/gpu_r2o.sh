@@ -1,0 +1,14 @@
+#!/bin/bash
+T=${1:-r2o}
+mkdir -p gpurun_out
+rm -f gpurun_out/${T}_knobs.log
+run() { echo "=== $1 $2" >> gpurun_out/${T}_knobs.log; env $1 python scripts/exp_c3.py $2 6 2>&1 | grep -E "frame 5|wave  [01]" >> gpurun_out/${T}_knobs.log; }
+run "NRB_STEP_LOOP=0" C4
+run "NRB_STEP_LOOP=1" C4
+run "NRB_STEP_LOOP=1 NRB_REFILL_PRIMARY=20" C4
+run "NRB_STEP_LOOP=0" C3
+run "NRB_STEP_LOOP=1" C3
+run "NRB_STEP_LOOP=0" C5
+( timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_golden.py -m gpu -q 2>&1 | tail -3 ) > gpurun_out/${T}_pytest.log
+( NRB_STEP_LOOP=1 timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_golden.py -m gpu -q 2>&1 | tail -3 ) >> gpurun_out/${T}_pytest.log
+cat gpurun_out/${T}_knobs.log; cat gpurun_out/${T}_pytest.log
