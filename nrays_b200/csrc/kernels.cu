@@ -322,6 +322,7 @@ struct LaneTrav {
   RayPre pre;
   int node, sp;
   float tbest;  // any: tmax (inclusive); closest: current best toi (exclusive)
+  int leaf;     // format 2 (speculative loop): postponed leaf code (< 0), or 0
 };
 constexpr int kLmO = 0, kLmD = 3, kLmPrim = 6, kLmU = 7, kLmV = 8, kLmSentinel = 9;  // then the stack proper
 constexpr int kLmSize = kLmSentinel + 1 + kStackSize;
@@ -343,59 +344,106 @@ NRB_DI void trav_start(LaneTrav &s, int *lm, int root, float tlimit) {
   s.sp = kLmSentinel;
   s.node = root;
   s.tbest = tlimit;
+  s.leaf = 0;
 }
 
+// One leaf of the traversal: up to 4 triangles (or one analytic shape).  Returns true if an any-hit query is finished.
+template <bool HAS_SHAPES>
+NRB_DI bool trav_leaf(const SceneView &sc, int leaf, int *lm, bool any, float &tbest) {
+  const uint32_t code = (uint32_t)~leaf;
+  const uint32_t first = code >> 3, cnt = ((code >> 1) & 3u) + 1u;
+  bool hit_any = false;
+  const V3 o = lm_vec(lm, kLmO), d = lm_vec(lm, kLmD);
+  if (HAS_SHAPES && (code & 1u)) {
+    Inter it;
+    if (cast_shape(sc.shapes[first], o, d, it) && (any ? it.toi <= tbest : it.toi < tbest)) {
+      tbest = it.toi;
+      lm_set_hit(lm, kShapeBit | first, it.u, it.v);
+      hit_any = any;
+    }
+  } else {
+    const float4 *tp = reinterpret_cast<const float4 *>(sc.tris + first);
+    for (uint32_t k = 0; k < cnt && !hit_any; ++k) {
+      float4 t0 = __ldg(tp + 3 * k), t1 = __ldg(tp + 3 * k + 1), t2 = __ldg(tp + 3 * k + 2);
+      float toi, bv, bw;
+      if (cast_tri_rt(mk(t0.x, t0.y, t0.z), mk(t1.x, t1.y, t1.z), mk(t2.x, t2.y, t2.z), o, d, tbest, any, toi, bv, bw)) {
+        tbest = toi;
+        lm_set_hit(lm, first + k, bv, bw);
+        hit_any = any;
+      }
+    }
+  }
+  return hit_any;
+}
+
+// One node visit: both children tested, the nearer one entered, the farther one pushed.
+template <int FMT>
+NRB_DI void trav_visit(const SceneView &sc, const RayPre &pre, float tbest, int &node, int &sp, int *lm) {
+  const NodeRec<FMT> n = load_node<FMT>(sc, node);
+  float c0min, c0max, c1min, c1max;
+  test_children(n, pre, tbest, c0min, c0max, c1min, c1max);
+  bool h0 = c0max >= c0min, h1 = c1max >= c1min;
+  if (!h0 && !h1) {
+    node = lm[sp--];
+  } else {
+    node = h0 ? n.c0 : n.c1;
+    if (h0 && h1) {
+      int far = n.c1;
+      if (c1min < c0min) {
+        far = n.c0;
+        node = n.c1;
+      }
+      lm[++sp] = far;
+    }
+  }
+}
+
+// Format 0 (coherent scenes): plain while-while — descend until a leaf, test it, repeat.
+// Format 2 (scenes beyond L2, whose rays diverge): SPECULATIVE while-while (Aila & Laine, HPG 2009).  In hair only ~11 of 32
+// lanes are in the node loop at any time (ncu, C4): a lane that reaches its leaf waits there for the slowest lane of the warp.
+// Here it postpones that leaf, pops the next node and keeps descending — with a not-yet-shrunk interval, which is conservative —
+// until no lane of the loop is still looking for its first leaf; then the postponed leaves (and a second one, if the lane
+// sits on one) are tested together.
 template <bool HAS_SHAPES, int FMT>
 NRB_DI void trav_run(const SceneView &sc, LaneTrav &s, int *lm, bool any, int min_active) {
   int node = s.node, sp = s.sp;
   float tbest = s.tbest;
-  while (node != kEmpty) {
-    while ((unsigned)node < (unsigned)kEmpty) {
-      const NodeRec<FMT> n = load_node<FMT>(sc, node);
-      float c0min, c0max, c1min, c1max;
-      test_children(n, s.pre, tbest, c0min, c0max, c1min, c1max);
-      bool h0 = c0max >= c0min, h1 = c1max >= c1min;
-      if (!h0 && !h1) {
+  if (FMT != 2) {
+    while (node != kEmpty) {
+      while ((unsigned)node < (unsigned)kEmpty) trav_visit<FMT>(sc, s.pre, tbest, node, sp, lm);
+      while (node < 0) node = trav_leaf<HAS_SHAPES>(sc, node, lm, any, tbest) ? kEmpty : lm[sp--];
+      if (__popc(__activemask()) < min_active) break;  // dynamic fetch: let the warp refill its idle lanes
+    }
+  } else {
+    int leaf = s.leaf;  // postponed leaf (< 0) or 0
+    while (node != kEmpty || leaf < 0) {
+      while ((unsigned)node < (unsigned)kEmpty) {
+        trav_visit<FMT>(sc, s.pre, tbest, node, sp, lm);
+        if (node < 0 && leaf == 0) {  // first leaf: postpone it and go on with the next node
+          leaf = node;
+          node = lm[sp--];
+        }
+        if (!__any_sync(__activemask(), leaf == 0)) break;  // every lane still descending holds a leaf: test them now
+      }
+      if (node < 0 && leaf == 0) {  // arrived on a leaf without descending (a root that is a leaf, or a popped leaf)
+        leaf = node;
         node = lm[sp--];
-      } else {
-        node = h0 ? n.c0 : n.c1;
-        if (h0 && h1) {
-          int far = n.c1;
-          if (c1min < c0min) {
-            far = n.c0;
-            node = n.c1;
-          }
-          lm[++sp] = far;
+      }
+      while (leaf < 0) {
+        if (trav_leaf<HAS_SHAPES>(sc, leaf, lm, any, tbest)) {
+          node = kEmpty;
+          leaf = 0;
+          break;
+        }
+        leaf = 0;
+        if (node < 0) {  // the lane stopped on a second leaf
+          leaf = node;
+          node = lm[sp--];
         }
       }
+      if (__popc(__activemask()) < min_active) break;
     }
-    while (node < 0) {
-      uint32_t code = (uint32_t)~node;
-      uint32_t first = code >> 3, cnt = ((code >> 1) & 3u) + 1u;
-      bool hit_any = false;
-      const V3 o = lm_vec(lm, kLmO), d = lm_vec(lm, kLmD);
-      if (HAS_SHAPES && (code & 1u)) {
-        Inter it;
-        if (cast_shape(sc.shapes[first], o, d, it) && (any ? it.toi <= tbest : it.toi < tbest)) {
-          tbest = it.toi;
-          lm_set_hit(lm, kShapeBit | first, it.u, it.v);
-          hit_any = any;
-        }
-      } else {
-        const float4 *tp = reinterpret_cast<const float4 *>(sc.tris + first);
-        for (uint32_t k = 0; k < cnt && !hit_any; ++k) {
-          float4 t0 = __ldg(tp + 3 * k), t1 = __ldg(tp + 3 * k + 1), t2 = __ldg(tp + 3 * k + 2);
-          float toi, bv, bw;
-          if (cast_tri_rt(mk(t0.x, t0.y, t0.z), mk(t1.x, t1.y, t1.z), mk(t2.x, t2.y, t2.z), o, d, tbest, any, toi, bv, bw)) {
-            tbest = toi;
-            lm_set_hit(lm, first + k, bv, bw);
-            hit_any = any;
-          }
-        }
-      }
-      node = hit_any ? kEmpty : lm[sp--];
-    }
-    if (__popc(__activemask()) < min_active) break;  // dynamic fetch: let the warp refill its idle lanes
+    s.leaf = leaf;
   }
   s.node = node, s.sp = sp, s.tbest = tbest;
 }

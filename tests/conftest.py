@@ -24,7 +24,12 @@ def _has_gpu():
 
 def pytest_collection_modifyitems(config, items):
     # -m gpu on a box without a device must fail loudly, not skip: the product has no CPU path.
-    pass
+    # A GPU test that hangs (a kernel that never ends) must not hold the box: pytest-timeout's thread method ends the
+    # process, which tears the CUDA context down.  No GPU test needs more than a minute; the limit is generous.
+    if config.pluginmanager.hasplugin("timeout"):
+        for item in items:
+            if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(600, method="thread"))
 
 
 @pytest.fixture(scope="session")

@@ -482,7 +482,7 @@ def test_tail_spill_bound_with_weak_attenuation(gpu):
 
 @pytest.mark.parametrize("env", [dict(NRB_TAIL_RAYS=0), dict(NRB_TAIL_RAYS=1 << 30), dict(NRB_SHADOW_CAP=4096),
                                  dict(NRB_BATCH_SLOTS=4096), dict(NRB_BATCH_SLOTS=4096, NRB_SHADOW_CAP=2048, NRB_TAIL_RAYS=64),
-                                 dict(NRB_REVERSE_SHADOW=0),
+                                 dict(NRB_REVERSE_SHADOW=0), dict(NRB_NODE_FORMAT=2), dict(NRB_NODE_FORMAT=2, NRB_REFILL_RAYS=24, NRB_REFILL_SHADOW=24),
                                  dict(NRB_REFILL_PRIMARY=20, NRB_REFILL_RAYS=24, NRB_REFILL_SHADOW=24),
                                  dict(NRB_REFILL_PRIMARY=31, NRB_REFILL_RAYS=31, NRB_REFILL_SHADOW=31, NRB_TAIL_RAYS=0)])
 def test_driver_paths_give_the_same_image(gpu, env):
@@ -495,6 +495,30 @@ def test_driver_paths_give_the_same_image(gpu, env):
     np.testing.assert_allclose(img, base, rtol=0, atol=3e-5)   # only the order of float atomics may differ
     assert st.as_dict()["rays_total"] == st0.as_dict()["rays_total"]
     assert_parity(img, ref, what=str(env), wh=(96, 80), twin=render_both.twin)
+
+
+@pytest.mark.timeout(120)
+def test_node_format_2_and_speculative_loop_on_small_scenes(gpu):
+    """Node format 2 (bf16 half extents, speculative while-while loop) is chosen for scenes beyond L2; forced here on scenes
+    whose traversal STARTS on a leaf (one shape, <= 4 triangles), on the shape zoo and on a mesh: same image as format 0."""
+    P1 = np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0]], np.float32)
+    scenes = [
+        ([node(Ball(1.0), NormalMaterial())], []),
+        ([node(TriMesh(P1, np.array([[0, 1, 2]], np.uint32), None), NormalMaterial())], []),
+        ([node(TriMesh(*quad_mesh(1.0, 1)), phong()), node(Plane((0, 1, 0)), phong(), pos=(0, -1, 0))], [Light((1, 4, -2), 0.0, 1, (1, 1, 1))]),
+        (zoo([phong(), phong(), phong(), phong(), phong()]), [Light((2, 4, -3), 0.0, 1, (1, 1, 1))]),
+        ([node(TriMesh(*quad_mesh(1.5, 6, y=0.3)), phong(), alpha=0.5, refr=1.2), node(TriMesh(*quad_mesh(3.0, 5, y=-0.5)), phong(), refl=(0.3, 0.4))],
+         [Light((0.5, 5, -1), 0.3, 4, (1, 1, 1))]),
+    ]
+    for k, (nodes, lights) in enumerate(scenes):
+        imgs = []
+        for fmt in (0, 2):
+            with _Env(NRB_NODE_FORMAT=fmt):
+                img, st, _, _ = render_both(nodes, lights, eye=(0.3, 1.5, -5.0), w=80, h=60, spp=2, window=1.0, seed=k)
+            imgs.append((img, st))
+        d = np.abs(imgs[0][0] - imgs[1][0]).max(axis=1)
+        assert (d > 1e-4).mean() < 5e-3, (k, float((d > 1e-4).mean()))   # identical hits up to exact ties / box rounding
+        assert abs(int(imgs[0][1].rays_total) - int(imgs[1][1].rays_total)) <= max(4, 2e-3 * imgs[0][1].rays_total), k
 
 
 def test_mesh_scene_driver_paths(gpu):
