@@ -792,7 +792,7 @@ int check_bvh(const HostScene &H, std::string &why) {
 // Device node formats: box centres + half extents (device_types.cuh "node formats").  The half extent is rounded up so
 // the device box contains the builder's [lo, hi] box — in fp32 for format 0, to bf16 for format 2.
 struct DevNodes {
-  std::vector<float> a;  // 16 words per node, every format (format 2 uses the first 12)
+  HostArray<float> a;  // 16 words per node, every format (format 2 uses the first 12)
 };
 
 struct NodeBoxes {  // one node's two child boxes as (centre, half extent), plus the child codes
@@ -837,27 +837,30 @@ NodeBoxes centre_half(const BvhNode &n, int format) {
 DevNodes to_device_nodes(const std::vector<BvhNode> &in, int format) {
   DevNodes d;
   const size_t wa = 16;
-  d.a.assign(in.size() * wa, 0.0f);
+  d.a.resize_uninit(in.size() * wa);
   auto put_int = [](float *dst, int v) { std::memcpy(dst, &v, 4); };
   auto put_u32 = [](float *dst, uint32_t v) { std::memcpy(dst, &v, 4); };
-  for (size_t i = 0; i < in.size(); ++i) {
-    const NodeBoxes nb = centre_half(in[i], format);
-    float *o = &d.a[i * wa];
-    if (format == 0) {
-      const float rec[12] = {nb.c[0][0], nb.c[0][1], nb.c[0][2], nb.c[1][0], nb.c[1][1], nb.c[1][2],
-                             nb.h[0][0], nb.h[0][1], nb.h[0][2], nb.h[1][0], nb.h[1][1], nb.h[1][2]};
-      std::memcpy(o, rec, sizeof(rec));
-      put_int(o + 12, nb.ch[0]), put_int(o + 13, nb.ch[1]);
-    } else {
-      const float rec[6] = {nb.c[0][0], nb.c[0][1], nb.c[1][0], nb.c[1][1], nb.c[0][2], nb.c[1][2]};
-      std::memcpy(o, rec, sizeof(rec));
-      put_u32(o + 6, bf16_pair(nb.h[0][0], nb.h[0][1]));
-      put_u32(o + 7, bf16_pair(nb.h[1][0], nb.h[1][1]));
-      float *ob = o + 8;
-      put_u32(ob, bf16_pair(nb.h[0][2], nb.h[1][2]));
-      put_int(ob + 1, nb.ch[0]), put_int(ob + 2, nb.ch[1]);
+  parallel_for(in.size(), [&](size_t lo_i, size_t hi_i) {
+    for (size_t i = lo_i; i < hi_i; ++i) {
+      const NodeBoxes nb = centre_half(in[i], format);
+      float *o = &d.a[i * wa];
+      std::memset(o, 0, wa * sizeof(float));
+      if (format == 0) {
+        const float rec[12] = {nb.c[0][0], nb.c[0][1], nb.c[0][2], nb.c[1][0], nb.c[1][1], nb.c[1][2],
+                               nb.h[0][0], nb.h[0][1], nb.h[0][2], nb.h[1][0], nb.h[1][1], nb.h[1][2]};
+        std::memcpy(o, rec, sizeof(rec));
+        put_int(o + 12, nb.ch[0]), put_int(o + 13, nb.ch[1]);
+      } else {
+        const float rec[6] = {nb.c[0][0], nb.c[0][1], nb.c[1][0], nb.c[1][1], nb.c[0][2], nb.c[1][2]};
+        std::memcpy(o, rec, sizeof(rec));
+        put_u32(o + 6, bf16_pair(nb.h[0][0], nb.h[0][1]));
+        put_u32(o + 7, bf16_pair(nb.h[1][0], nb.h[1][1]));
+        float *ob = o + 8;
+        put_u32(ob, bf16_pair(nb.h[0][2], nb.h[1][2]));
+        put_int(ob + 1, nb.ch[0]), put_int(ob + 2, nb.ch[1]);
+      }
     }
-  }
+  });
   return d;
 }
 
@@ -1478,8 +1481,10 @@ int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOp
     std::string why;
     if (check_bvh(H, why) || check_device_nodes(H, why)) return fail(NRB_ERR_INTERNAL, "internal BVH invariant violated: " + why);
   }
+  PhaseTimer upt;
   rc = upload_scene(*desc, H, *S);
   if (rc) return rc;
+  upt.lap("device format + upload");
   S->build_info.bvh_nodes = H.nodes.size();
   S->build_info.triangles = H.n_source_tris;
   S->build_info.shapes = H.shapes.size();

@@ -176,18 +176,49 @@ struct BuildClock {  // NRB_BUILD_TIMES=1: host-side phases of the device builde
   }
 };
 
+// Device scratch for one build: ONE allocation carved into aligned pieces.  (Two dozen separate cudaMalloc / cudaFree calls
+// cost 50-80 ms on this part — several times the build kernels themselves.)  Usage: reserve() every piece, commit(), then take().
 struct Scratch {
-  std::vector<void *> ptrs;
+  struct Piece {
+    void **slot;
+    size_t bytes;
+  };
+  std::vector<Piece> pieces;
+  char *base = nullptr;
   ~Scratch() {
-    for (void *p : ptrs) cudaFree(p);
+    release_extra();
+    if (base) cudaFree(base);
   }
+  template <class T>
+  void reserve(T **p, size_t n) {
+    *p = nullptr;
+    pieces.push_back(Piece{reinterpret_cast<void **>(p), (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255});
+  }
+  cudaError_t commit() {
+    size_t total = 0;
+    for (const Piece &pc : pieces) total += pc.bytes;
+    cudaError_t e = cudaMalloc((void **)&base, total);
+    if (e != cudaSuccess) return e;
+    size_t off = 0;
+    for (const Piece &pc : pieces) {
+      *pc.slot = base + off;
+      off += pc.bytes;
+    }
+    return cudaSuccess;
+  }
+  // late, data-dependent pieces (output nodes): their own allocation, freed with the rest
+  std::vector<void *> extra;
   template <class T>
   cudaError_t alloc(T **p, size_t n) {
     void *q = nullptr;
     cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
-    if (e == cudaSuccess) ptrs.push_back(q);
+    if (e == cudaSuccess) extra.push_back(q);
     *p = reinterpret_cast<T *>(q);
     return e;
+  }
+  void release_extra() {
+    for (void *q : extra) cudaFree(q);
+    extra.clear();
   }
 };
 
@@ -215,22 +246,28 @@ cudaError_t lbvh_build(const Box *h_boxes, uint32_t n, std::vector<BvhNode> &nod
   uint32_t *d_vals, *d_vals2;
   int *d_left, *d_right, *d_lo, *d_hi, *d_pi, *d_pl, *d_height, *d_flags, *d_emit, *d_new;
   BvhNode *d_out;
-  LB_CU(sc.alloc(&d_boxes, n));
-  LB_CU(sc.alloc(&d_node_box, n));
-  LB_CU(sc.alloc(&d_keys, n));
-  LB_CU(sc.alloc(&d_keys2, n));
-  LB_CU(sc.alloc(&d_vals, n));
-  LB_CU(sc.alloc(&d_vals2, n));
-  LB_CU(sc.alloc(&d_left, n));
-  LB_CU(sc.alloc(&d_right, n));
-  LB_CU(sc.alloc(&d_lo, n));
-  LB_CU(sc.alloc(&d_hi, n));
-  LB_CU(sc.alloc(&d_pi, n));
-  LB_CU(sc.alloc(&d_pl, n));
-  LB_CU(sc.alloc(&d_height, n));
-  LB_CU(sc.alloc(&d_flags, n));
-  LB_CU(sc.alloc(&d_emit, n));
-  LB_CU(sc.alloc(&d_new, n));
+  sc.reserve(&d_boxes, n);
+  sc.reserve(&d_node_box, n);
+  sc.reserve(&d_keys, n);
+  sc.reserve(&d_keys2, n);
+  sc.reserve(&d_vals, n);
+  sc.reserve(&d_vals2, n);
+  sc.reserve(&d_left, n);
+  sc.reserve(&d_right, n);
+  sc.reserve(&d_lo, n);
+  sc.reserve(&d_hi, n);
+  sc.reserve(&d_pi, n);
+  sc.reserve(&d_pl, n);
+  sc.reserve(&d_height, n);
+  sc.reserve(&d_flags, n);
+  sc.reserve(&d_emit, n);
+  sc.reserve(&d_new, n);
+  size_t sort_bytes = 0, scan_bytes = 0;
+  LB_CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63));
+  LB_CU(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_emit, d_new, (int)(n - 1)));
+  char *d_tmp;
+  sc.reserve(&d_tmp, std::max(sort_bytes, scan_bytes));
+  LB_CU(sc.commit());
   LB_CU(cudaMemcpy(d_boxes, h_boxes, sizeof(DBox) * n, cudaMemcpyHostToDevice));
   cudaEvent_t e0, e1;
   LB_CU(cudaEventCreate(&e0));
@@ -240,25 +277,13 @@ cudaError_t lbvh_build(const Box *h_boxes, uint32_t n, std::vector<BvhNode> &nod
   std::memcpy(&scene, &rb, sizeof(scene));
   const int T = 256;
   k_morton<<<(n + T - 1) / T, T>>>(d_boxes, n, scene, d_keys, d_vals);
-  {
-    size_t tmp_bytes = 0;
-    LB_CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63));
-    char *d_tmp;
-    LB_CU(sc.alloc(&d_tmp, tmp_bytes));
-    LB_CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63));
-  }
+  LB_CU(cub::DeviceRadixSort::SortPairs(d_tmp, sort_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63));
   LB_CU(cudaMemset(d_flags, 0, sizeof(int) * n));
   LB_CU(cudaMemset(d_height, 0, sizeof(int) * n));
   k_tree<<<(n - 1 + T - 1) / T, T>>>(d_keys2, (int)n, d_left, d_right, d_lo, d_hi, d_pi, d_pl);
   k_fit<<<(n + T - 1) / T, T>>>(d_boxes, d_vals2, (int)n, d_left, d_right, d_lo, d_hi, d_pi, d_pl, d_node_box, d_height, d_flags);
   k_flag<<<(n - 1 + T - 1) / T, T>>>(d_lo, d_hi, (int)n, d_emit);
-  {
-    size_t tmp_bytes = 0;
-    LB_CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_emit, d_new, (int)(n - 1)));
-    char *d_tmp;
-    LB_CU(sc.alloc(&d_tmp, tmp_bytes));
-    LB_CU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_emit, d_new, (int)(n - 1)));
-  }
+  LB_CU(cub::DeviceScan::ExclusiveSum(d_tmp, scan_bytes, d_emit, d_new, (int)(n - 1)));
   int last_new = 0, last_emit = 0, h_height = 0;
   LB_CU(cudaMemcpy(&last_new, d_new + (n - 2), sizeof(int), cudaMemcpyDeviceToHost));
   LB_CU(cudaMemcpy(&last_emit, d_emit + (n - 2), sizeof(int), cudaMemcpyDeviceToHost));
@@ -449,38 +474,39 @@ cudaError_t ploc_build(const Box *h_boxes, uint32_t n, int radius, std::vector<B
   int *d_cid[2], *d_nn, *d_left, *d_right, *d_count, *d_height, *d_offset, *d_emit, *d_new, *d_leaf, *d_inside;
   float *d_cost;
   const size_t n_nodes = 2 * (size_t)n;
-  LB_CU(sc.alloc(&d_boxes, n));
-  LB_CU(sc.alloc(&d_cbox[0], n));
-  LB_CU(sc.alloc(&d_cbox[1], n));
-  LB_CU(sc.alloc(&d_node_box, n_nodes));
-  LB_CU(sc.alloc(&d_keys, n));
-  LB_CU(sc.alloc(&d_keys2, n));
-  LB_CU(sc.alloc(&d_flag, n));
-  LB_CU(sc.alloc(&d_scan, n));
-  LB_CU(sc.alloc(&d_vals, n));
-  LB_CU(sc.alloc(&d_vals2, n));
-  LB_CU(sc.alloc(&d_order, n));
-  LB_CU(sc.alloc(&d_cid[0], n));
-  LB_CU(sc.alloc(&d_cid[1], n));
-  LB_CU(sc.alloc(&d_nn, n));
-  LB_CU(sc.alloc(&d_left, n_nodes));
-  LB_CU(sc.alloc(&d_right, n_nodes));
-  LB_CU(sc.alloc(&d_count, n_nodes));
-  LB_CU(sc.alloc(&d_height, n_nodes));
-  LB_CU(sc.alloc(&d_offset, n_nodes));
-  LB_CU(sc.alloc(&d_leaf, n_nodes));
-  LB_CU(sc.alloc(&d_inside, n_nodes));
-  LB_CU(sc.alloc(&d_cost, n_nodes));
-  LB_CU(sc.alloc(&d_emit, n));
-  LB_CU(sc.alloc(&d_new, n));
-  LB_CU(cudaMemset(d_leaf, 0, sizeof(int) * n_nodes));
-  LB_CU(cudaMemset(d_inside, 0, sizeof(int) * n_nodes));
+  sc.reserve(&d_boxes, n);
+  sc.reserve(&d_cbox[0], n);
+  sc.reserve(&d_cbox[1], n);
+  sc.reserve(&d_node_box, n_nodes);
+  sc.reserve(&d_keys, n);
+  sc.reserve(&d_keys2, n);
+  sc.reserve(&d_flag, n);
+  sc.reserve(&d_scan, n);
+  sc.reserve(&d_vals, n);
+  sc.reserve(&d_vals2, n);
+  sc.reserve(&d_order, n);
+  sc.reserve(&d_cid[0], n);
+  sc.reserve(&d_cid[1], n);
+  sc.reserve(&d_nn, n);
+  sc.reserve(&d_left, n_nodes);
+  sc.reserve(&d_right, n_nodes);
+  sc.reserve(&d_count, n_nodes);
+  sc.reserve(&d_height, n_nodes);
+  sc.reserve(&d_offset, n_nodes);
+  sc.reserve(&d_leaf, n_nodes);
+  sc.reserve(&d_inside, n_nodes);
+  sc.reserve(&d_cost, n_nodes);
+  sc.reserve(&d_emit, n);
+  sc.reserve(&d_new, n);
   size_t scan_bytes = 0, sort_bytes = 0, scan2_bytes = 0;
   LB_CU(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flag, d_scan, (int)n));
   LB_CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63));
   LB_CU(cub::DeviceScan::ExclusiveSum(nullptr, scan2_bytes, d_emit, d_new, (int)n));
   char *d_tmp;
-  LB_CU(sc.alloc(&d_tmp, std::max(std::max(scan_bytes, sort_bytes), scan2_bytes)));
+  sc.reserve(&d_tmp, std::max(std::max(scan_bytes, sort_bytes), scan2_bytes));
+  LB_CU(sc.commit());
+  LB_CU(cudaMemset(d_leaf, 0, sizeof(int) * n_nodes));
+  LB_CU(cudaMemset(d_inside, 0, sizeof(int) * n_nodes));
   unsigned long long *h_last = nullptr;  // pinned: (scan, key) of the last cluster of the round
   LB_CU(cudaHostAlloc((void **)&h_last, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
   struct Unpin {
