@@ -19,7 +19,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
 XM=lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum,lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum,lts__t_sectors_srcunit_tex_op_write_lookup_miss.sum,lts__t_sectors_srcunit_tex_op_red_lookup_miss.sum,lts__t_sectors_srcunit_tex_lookup_miss.sum,lts__t_sectors_srcunit_ltcfabric_lookup_miss.sum,lts__t_sectors_srcunit_ltcfabric.sum,lts__t_sectors_lookup_miss.sum,lts__t_sectors.sum,l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum,l1tex__t_sectors_pipe_lsu_mem_local_op_ld_lookup_miss.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum,lts__t_sectors_srcunit_tex_aperture_device_lookup_miss.sum,lts__t_sectors_srcunit_tex_aperture_peer_lookup_miss.sum,l1tex__data_pipe_lsu_wavefronts.sum,l1tex__data_pipe_lsu_wavefronts_mem_lg.sum,smsp__inst_executed.sum
 timeout 900 ncu --set full --metrics $XM --clock-control none --import-source on -k regex:"trace_kernel|shade_kernel|tail_kernel" -s 7 -c 7 \
     -o gpurun_out/${T}_prof_c3 -f python scripts/exp_c3.py C3 3 > gpurun_out/${T}_ncu_c3.log 2>&1
-timeout 900 ncu --set full --metrics $XM --clock-control none --import-source on -k regex:"trace_kernel|shade_kernel|tail_kernel" -s 4 -c 4 \
+timeout 900 ncu --set full --metrics $XM --clock-control none --import-source on -k regex:"trace_kernel|shade_kernel|tail_kernel" -s 3 -c 3 \
     -o gpurun_out/${T}_prof_c4 -f python scripts/exp_c3.py C4 2 > gpurun_out/${T}_ncu_c4.log 2>&1
 for cfg in C3 C4 C2 C1; do
   echo "=== $cfg" >> gpurun_out/${T}_configs.log
