@@ -186,7 +186,7 @@ namespace {
 bool shape_has_uv(int kind) { return kind == NRB_SHAPE_BALL || kind == NRB_SHAPE_CUBOID || kind == NRB_SHAPE_TRIMESH; }
 
 int relayout_bfs(std::vector<BvhNode> &nodes, int &root_all, int &root_opaque, std::vector<Candidate> &cands,
-                 std::vector<Candidate> &nmaps) {
+                 std::vector<Candidate> &nmaps, const std::vector<char> &dead) {
   // Level-order relabel from root_all so the top of the tree is one contiguous prefix of the array
   // (what the closest-hit kernel touches for every ray; also the part worth staging on chip).
   if (nodes.empty()) return 0;
@@ -220,7 +220,7 @@ int relayout_bfs(std::vector<BvhNode> &nodes, int &root_all, int &root_opaque, s
     // everything not placed yet that is reachable: sweep in builder order (children of placed nodes are reachable by construction;
     // unreachable nodes do not exist — every builder node hangs off root_all or an nmap root)
     for (size_t i = 0; i < nodes.size(); ++i)
-      if (remap[i] < 0) {
+      if (remap[i] < 0 && !(i < dead.size() && dead[i])) {  // dead: tops of device-built trees replaced by a SAH top
         remap[i] = (int)order.size();
         order.push_back((int)i);
       }
@@ -548,7 +548,74 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
         for (size_t k = lo_t; k < hi_t; ++k) bb.tri_order[(size_t)tri_off + k] = (uint32_t)items[order[k]].payload;
       });
       *code = shift(root);
-      bb.max_depth_seen = std::max(bb.max_depth_seen, depth + 1);
+      const int prev_depth = bb.max_depth_seen;
+      bb.max_depth_seen = std::max(prev_depth, depth + 1);
+      // ---- SAH top ----------------------------------------------------------------------------------------------------
+      // Morton-ordered builders place the BOTTOM of the tree well (neighbouring triangles end up together) and the TOP badly
+      // (LBVH: splits dictated by Morton prefixes; PLOC: agglomeration knows nothing about the rays' long walks through an
+      // atrium): 48 / 40 node visits per primary ray on C3 against 28 for the host SAH tree.  So the device tree is cut where
+      // its subtrees hold <= T triangles and the host's binned-SAH builder rebuilds everything above the cut over those few
+      // thousand subtree boxes (milliseconds).  NRB_RESAH_TOP=0 keeps the device tree as built.
+      if (env_size("NRB_RESAH_TOP", 1) != 0 && *code >= 0) {
+        const size_t n_sub = sub.size();
+        // triangles below every spliced node (iterative post-order from the root)
+        std::vector<uint32_t> cnt(n_sub, 0);
+        auto leaf_count = [](int c) -> uint32_t { return (((uint32_t)~c >> 1) & 3u) + 1u; };
+        {
+          std::vector<std::pair<int, int>> st;  // (local node, state)
+          st.emplace_back(*code - node_off, 0);
+          while (!st.empty()) {
+            auto &top = st.back();
+            const BvhNode &nd = bb.nodes[(size_t)node_off + top.first];
+            if (top.second == 0) {
+              top.second = 1;
+              if (nd.n3.x >= 0) st.emplace_back(nd.n3.x - node_off, 0);
+              if (nd.n3.y >= 0) st.emplace_back(nd.n3.y - node_off, 0);
+            } else {
+              const uint32_t a = nd.n3.x >= 0 ? cnt[nd.n3.x - node_off] : leaf_count(nd.n3.x);
+              const uint32_t b = nd.n3.y >= 0 ? cnt[nd.n3.y - node_off] : leaf_count(nd.n3.y);
+              cnt[top.first] = a + b;
+              st.pop_back();
+            }
+          }
+        }
+        const uint32_t total = cnt[*code - node_off];
+        // cut size: ~65 k subtrees for meshes up to 1 M triangles, ~33 k beyond (C3: T = 4 -> 2.39 ms against 2.23 for the host
+        // SAH tree, 2.94 as built; C4: T = 88 -> 7.75 ms against 7.28, 8.02 as built; the SAH top costs 30-150 ms of host time)
+        const uint32_t T = (uint32_t)env_size("NRB_RESAH_LEAF", std::max<size_t>(4, total / (total <= (1u << 20) ? 65536u : 32768u)));
+        if (total > 2 * T) {
+          std::vector<BuildItem> cut;
+          std::vector<int> walk{*code - node_off};
+          while (!walk.empty()) {
+            const int li = walk.back();
+            walk.pop_back();
+            const BvhNode nd = bb.nodes[(size_t)node_off + li];
+            bb.dead.resize(bb.nodes.size(), 0);
+            bb.dead[(size_t)node_off + li] = 1;  // every node above the cut is replaced by the SAH top
+            const Box b0{{nd.n0.x, nd.n0.z, nd.n2.x}, {nd.n0.y, nd.n0.w, nd.n2.y}}, b1{{nd.n1.x, nd.n1.z, nd.n2.z}, {nd.n1.y, nd.n1.w, nd.n2.w}};
+            const int ch[2] = {nd.n3.x, nd.n3.y};
+            const Box *bx[2] = {&b0, &b1};
+            for (int k = 0; k < 2; ++k) {
+              if (ch[k] >= 0 && cnt[ch[k] - node_off] > T) walk.push_back(ch[k] - node_off);
+              else cut.push_back(BuildItem{*bx[k], ch[k]});
+            }
+          }
+          *code = bb.build_payloads(cut, rb);
+          // true depth of the rebuilt tree (levels of inner nodes on the longest path): SAH top + the device subtree below it
+          int deepest = 0;
+          std::vector<std::pair<int, int>> st{{*code, 1}};
+          while (!st.empty()) {
+            const auto [c, lvl] = st.back();
+            st.pop_back();
+            if (c < 0) continue;
+            deepest = std::max(deepest, lvl);
+            const BvhNode &nd = bb.nodes[(size_t)c];
+            st.emplace_back(nd.n3.x, lvl + 1);
+            st.emplace_back(nd.n3.y, lvl + 1);
+          }
+          bb.max_depth_seen = std::max(prev_depth, deepest);
+        }
+      }
       return NRB_OK;
     }
     *code = bb.build_triangles(items, rb);
@@ -705,7 +772,7 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
     return fail(NRB_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
   if (nmaps.size() > 32) return fail(NRB_ERR_UNSUPPORTED, "more than 32 nodes with a depth-shift (nmap) texture");
   pt.lap("candidate / top trees");
-  relayout_bfs(bb.nodes, root_all, root_opaque, candidates, nmaps);
+  relayout_bfs(bb.nodes, root_all, root_opaque, candidates, nmaps, bb.dead);
   pt.lap("level-order relayout");
 
   // leaf-ordered triangle arrays
@@ -904,6 +971,22 @@ int check_device_nodes(const HostScene &H, std::string &why) {
     }
   }
   return 0;
+}
+
+// NRB_DUMP_BVH=<file>: builder experiments (scripts/bvh_sim.cpp) — nodes + leaf-ordered triangles + candidates as built
+void dump_bvh(const HostScene &H) {
+  const char *path = getenv("NRB_DUMP_BVH");
+  if (!path) return;
+  if (FILE *f = fopen(path, "wb")) {
+    uint64_t hdr[4] = {H.nodes.size(), H.tris.size(), (uint64_t)(uint32_t)H.root_all, (uint64_t)(uint32_t)H.root_opaque};
+    fwrite(hdr, sizeof(hdr), 1, f);
+    fwrite(H.nodes.data(), sizeof(BvhNode), H.nodes.size(), f);
+    fwrite(H.tris.data(), sizeof(Tri), H.tris.size(), f);
+    uint64_t nc = H.candidates.size();
+    fwrite(&nc, sizeof(nc), 1, f);
+    fwrite(H.candidates.data(), sizeof(Candidate), H.candidates.size(), f);
+    fclose(f);
+  }
 }
 
 int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
@@ -1481,6 +1564,7 @@ int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOp
     std::string why;
     if (check_bvh(H, why) || check_device_nodes(H, why)) return fail(NRB_ERR_INTERNAL, "internal BVH invariant violated: " + why);
   }
+  dump_bvh(H);
   PhaseTimer upt;
   rc = upload_scene(*desc, H, *S);
   if (rc) return rc;
@@ -1520,18 +1604,7 @@ int nrb_scene_validate(const NrbSceneDesc *desc, NrbBuildInfo *info) {
   double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   std::string why;
   if (check_bvh(H, why) || check_device_nodes(H, why)) return fail(NRB_ERR_INTERNAL, "internal BVH invariant violated: " + why);
-  if (const char *path = getenv("NRB_DUMP_BVH")) {  // builder experiments (scripts/bvh_sim.cpp): nodes + triangles as built
-    if (FILE *f = fopen(path, "wb")) {
-      uint64_t hdr[4] = {H.nodes.size(), H.tris.size(), (uint64_t)(uint32_t)H.root_all, (uint64_t)(uint32_t)H.root_opaque};
-      fwrite(hdr, sizeof(hdr), 1, f);
-      fwrite(H.nodes.data(), sizeof(BvhNode), H.nodes.size(), f);
-      fwrite(H.tris.data(), sizeof(Tri), H.tris.size(), f);
-      uint64_t nc = H.candidates.size();  // trailer: the shadow structure's transparent candidates
-      fwrite(&nc, sizeof(nc), 1, f);
-      fwrite(H.candidates.data(), sizeof(Candidate), H.candidates.size(), f);
-      fclose(f);
-    }
-  }
+  dump_bvh(H);
   if (info) {
     std::memset(info, 0, sizeof(*info));
     info->bvh_nodes = H.nodes.size();

@@ -43,6 +43,7 @@ struct BuildItem {
 struct BvhBuilder {
   std::vector<BvhNode> nodes;      // shared node pool (all builds append here)
   std::vector<uint32_t> tri_order; // leaf-ordered triangle indices (triangle builds append here)
+  std::vector<char> dead;          // nodes of the pool that were replaced (tops of device-built trees, api.cu) and must not be laid out
   int max_depth_seen = 0;
 
   // Builds a tree over triangles; leaves hold up to kMaxLeafTris consecutive entries of tri_order.
