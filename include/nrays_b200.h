@@ -207,6 +207,9 @@ typedef struct NrbBuildInfo {
   float build_ms;      /* host wall time of flatten + BVH build (+ upload for nrb_scene_create*) */
   float gpu_build_ms;  /* CUDA-event time of the device build kernels (NRB_BUILDER_LBVH), else 0 */
   uint32_t builder;    /* NRB_BUILDER_* actually used */
+  uint32_t node_format; /* device node record the scene was uploaded in: 0 fp32 (64 B), 2 bf16 half extents (48 B),
+                           3 / 4 16-bit grid (32 B), plain / speculative loop; 0 from nrb_scene_validate (nothing uploaded) */
+  uint32_t _pad;
 } NrbBuildInfo;
 int nrb_scene_validate(const NrbSceneDesc *desc, NrbBuildInfo *info);
 

@@ -180,6 +180,8 @@ class NrbBuildInfo(C.Structure):
         ("build_ms", C.c_float),
         ("gpu_build_ms", C.c_float),
         ("builder", C.c_uint32),
+        ("node_format", C.c_uint32),
+        ("_pad", C.c_uint32),
     ]
 
 

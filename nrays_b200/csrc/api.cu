@@ -859,8 +859,45 @@ int check_bvh(const HostScene &H, std::string &why) {
 // Device node formats: box centres + half extents (device_types.cuh "node formats").  The half extent is rounded up so
 // the device box contains the builder's [lo, hi] box — in fp32 for format 0, to bf16 for format 2.
 struct DevNodes {
-  HostArray<float> a;  // 16 words per node, every format (format 2 uses the first 12)
+  HostArray<float> a;  // 16 words per node for formats 0 / 2 (format 2 uses the first 12), 8 words for the grid format 3
 };
+
+// Format 3: ONE 16-bit grid over every box of the scene.  A plane at cell q sits at lo + q * cell; boxes are snapped outward
+// and widened by one more cell, which covers the kernel's arithmetic (kernels.cu: ray_pre_for<3> folds 2^23 * cell / d into the
+// ray constant: at most 0.52 cell of rounding, see check_device_nodes).  Unbounded or absurdly large boxes have no grid.
+struct NodeGrid {
+  float lo[3], cell[3];
+  bool ok;
+};
+constexpr int kGridMargin = 16;  // cells left free at both ends of the grid
+constexpr double kGridCells = 65535.0 - 2.0 * kGridMargin;
+
+NodeGrid make_node_grid(const std::vector<BvhNode> &in) {
+  NodeGrid g;
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (const BvhNode &n : in) {
+    const float l[3] = {std::min(n.n0.x, n.n1.x), std::min(n.n0.z, n.n1.z), std::min(n.n2.x, n.n2.z)};
+    const float h[3] = {std::max(n.n0.y, n.n1.y), std::max(n.n0.w, n.n1.w), std::max(n.n2.y, n.n2.w)};
+    for (int k = 0; k < 3; ++k) lo[k] = std::min(lo[k], l[k]), hi[k] = std::max(hi[k], h[k]);
+  }
+  g.ok = !in.empty();
+  for (int k = 0; k < 3; ++k) {
+    if (!(lo[k] <= hi[k]) || !(std::fabs(lo[k]) < 1.0e9f) || !(std::fabs(hi[k]) < 1.0e9f)) g.ok = false;
+    const double ext = std::max((double)hi[k] - (double)lo[k], 1.0e-12 + 1.0e-6 * std::max(std::fabs((double)lo[k]), std::fabs((double)hi[k])));
+    g.cell[k] = (float)(ext / (kGridCells - 4.0));  // float rounding of cell / lo must not push a box off the grid
+    g.lo[k] = (float)((double)lo[k] - (kGridMargin + 2.0) * (double)g.cell[k]);
+  }
+  return g;
+}
+
+// (lo, hi) -> cells, outward plus one; false if the box leaves the grid (cannot happen for boxes make_node_grid has seen)
+bool grid_cells(const NodeGrid &g, int k, float lo, float hi, uint32_t &qlo, uint32_t &qhi) {
+  const double a = std::floor(((double)lo - (double)g.lo[k]) / (double)g.cell[k]) - 1.0;
+  const double b = std::ceil(((double)hi - (double)g.lo[k]) / (double)g.cell[k]) + 1.0;
+  if (!(a >= 0.0) || !(b <= 65535.0) || !(a <= b)) return false;
+  qlo = (uint32_t)a, qhi = (uint32_t)b;
+  return true;
+}
 
 struct NodeBoxes {  // one node's two child boxes as (centre, half extent), plus the child codes
   float c[2][3], h[2][3];
@@ -901,16 +938,30 @@ NodeBoxes centre_half(const BvhNode &n, int format) {
   return o;
 }
 
-DevNodes to_device_nodes(const std::vector<BvhNode> &in, int format) {
+DevNodes to_device_nodes(const std::vector<BvhNode> &in, int format, const NodeGrid *grid = nullptr, bool *grid_failed = nullptr) {
   DevNodes d;
-  const size_t wa = 16;
+  const size_t wa = format >= 3 ? 8 : 16;
   d.a.resize_uninit(in.size() * wa);
   auto put_int = [](float *dst, int v) { std::memcpy(dst, &v, 4); };
   auto put_u32 = [](float *dst, uint32_t v) { std::memcpy(dst, &v, 4); };
+  std::atomic<bool> off_grid{false};
   parallel_for(in.size(), [&](size_t lo_i, size_t hi_i) {
     for (size_t i = lo_i; i < hi_i; ++i) {
-      const NodeBoxes nb = centre_half(in[i], format);
       float *o = &d.a[i * wa];
+      if (format >= 3) {
+        const BvhNode &n = in[i];
+        const float lo[2][3] = {{n.n0.x, n.n0.z, n.n2.x}, {n.n1.x, n.n1.z, n.n2.z}};
+        const float hi[2][3] = {{n.n0.y, n.n0.w, n.n2.y}, {n.n1.y, n.n1.w, n.n2.w}};
+        for (int b = 0; b < 2; ++b)
+          for (int k = 0; k < 3; ++k) {
+            uint32_t ql = 65535u, qh = 0u;
+            if (!grid_cells(*grid, k, lo[b][k], hi[b][k], ql, qh)) off_grid = true;
+            put_u32(o + 3 * b + k, (qh << 16) | ql);
+          }
+        put_int(o + 6, n.n3.x), put_int(o + 7, n.n3.y);
+        continue;
+      }
+      const NodeBoxes nb = centre_half(in[i], format);
       std::memset(o, 0, wa * sizeof(float));
       if (format == 0) {
         const float rec[12] = {nb.c[0][0], nb.c[0][1], nb.c[0][2], nb.c[1][0], nb.c[1][1], nb.c[1][2],
@@ -928,6 +979,7 @@ DevNodes to_device_nodes(const std::vector<BvhNode> &in, int format) {
       }
     }
   });
+  if (grid_failed) *grid_failed = off_grid.load();
   return d;
 }
 
@@ -936,7 +988,7 @@ NodeBoxes decode_device_node(const DevNodes &d, size_t i, int format) {
   NodeBoxes o;
   auto get_int = [](const float *src) { int v; std::memcpy(&v, src, 4); return v; };
   auto bf_lo = [](const float *src) { uint32_t u; std::memcpy(&u, src, 4); u <<= 16; float r; std::memcpy(&r, &u, 4); return r; };
-  auto bf_hi = [](const float *src) { uint32_t u; std::memcpy(&u, src, 4); u &= 0xFFFF0000u; float r; std::memcpy(&r, &u, 4); return r; };
+  auto bf_hi = [](const float *src) { float r; std::memcpy(&r, src, 4); return r; };  // the kernel does not mask the low half away
   if (format == 0) {
     const float *p = &d.a[i * 16];
     for (int k = 0; k < 3; ++k) o.c[0][k] = p[k], o.c[1][k] = p[3 + k], o.h[0][k] = p[6 + k], o.h[1][k] = p[9 + k];
@@ -970,6 +1022,28 @@ int check_device_nodes(const HostScene &H, std::string &why) {
       if (d.ch[0] != n.n3.x || d.ch[1] != n.n3.y) return why = "device node lost its child codes", 1;
     }
   }
+  // format 3: every plane at least half a cell outside the builder's box (the kernel's rounding budget), on the grid
+  const NodeGrid g = make_node_grid(H.nodes);
+  if (g.ok) {
+    bool failed = false;
+    const DevNodes dev = to_device_nodes(H.nodes, 3, &g, &failed);
+    if (failed) return why = "node box off the 16-bit grid", 1;
+    for (size_t i = 0; i < H.nodes.size(); ++i) {
+      const BvhNode &n = H.nodes[i];
+      const float lo[2][3] = {{n.n0.x, n.n0.z, n.n2.x}, {n.n1.x, n.n1.z, n.n2.z}};
+      const float hi[2][3] = {{n.n0.y, n.n0.w, n.n2.y}, {n.n1.y, n.n1.w, n.n2.w}};
+      uint32_t w[8];
+      std::memcpy(w, &dev.a[i * 8], 32);
+      for (int b = 0; b < 2; ++b)
+        for (int k = 0; k < 3; ++k) {
+          const double pl = (double)g.lo[k] + (double)(w[3 * b + k] & 0xFFFFu) * (double)g.cell[k];
+          const double ph = (double)g.lo[k] + (double)(w[3 * b + k] >> 16) * (double)g.cell[k];
+          if (!(pl + 0.75 * (double)g.cell[k] <= (double)lo[b][k]) || !(ph - 0.75 * (double)g.cell[k] >= (double)hi[b][k]))
+            return why = "grid box (node format 3) does not contain the builder's box with its margin", 1;
+        }
+      if ((int)w[6] != n.n3.x || (int)w[7] != n.n3.y) return why = "device node (format 3) lost its child codes", 1;
+    }
+  }
   return 0;
 }
 
@@ -994,13 +1068,22 @@ int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
   // every lane fetches its own cache line — use the 48-byte-per-visit bf16 form.  Depth-shift (nmap) scenes run the general
   // kernel, compiled for format 0 only.  NRB_NODE_FORMAT=0|2 overrides (experiments).
   const uint64_t geom_bytes = H.nodes.size() * 64ull + H.tris.size() * sizeof(Tri);
-  int nfmt = (geom_bytes > (96ull << 20) && H.nmaps.empty()) ? 2 : 0;
+  const bool grid_capable = H.shapes.empty() && H.nmaps.empty() && !H.nodes.empty();  // formats 3 / 4: mesh-only scenes
+  int nfmt = (geom_bytes > (96ull << 20) && H.nmaps.empty()) ? (grid_capable ? 4 : 2) : 0;
   if (const char *e = getenv("NRB_NODE_FORMAT")) {
     const int f = atoi(e);
     if ((f == 0 || f == 2) && (H.nmaps.empty() || f == 0)) nfmt = f;
+    if ((f == 3 || f == 4) && grid_capable) nfmt = f;
+  }
+  NodeGrid grid = {};
+  if (nfmt >= 3) {
+    grid = make_node_grid(H.nodes);
+    if (!grid.ok) nfmt = nfmt == 4 ? 2 : 0;
   }
   {
-    const DevNodes dn = to_device_nodes(H.nodes, nfmt);
+    bool off_grid = false;
+    const DevNodes dn = to_device_nodes(H.nodes, nfmt, &grid, &off_grid);
+    if (off_grid) return fail(NRB_ERR_INTERNAL, "internal BVH invariant violated: node box off the 16-bit grid");
     CU(upload(S.d_nodes, dn.a));
   }
   CU(upload(S.d_tris, H.tris));
@@ -1021,6 +1104,7 @@ int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
   SceneView &v = S.view;
   v.nodes = S.d_nodes.p;
   v.node_format = nfmt;
+  for (int k = 0; k < 3; ++k) v.grid_lo[k] = grid.lo[k], v.grid_cell[k] = grid.cell[k];
   v.tris = S.d_tris.as<Tri>();
   v.tri_uvs = S.d_tri_uvs.as<TriUV>();
   v.shapes = S.d_shapes.as<Shape>();
@@ -1046,7 +1130,7 @@ int upload_scene(const NrbSceneDesc &d, const HostScene &H, NrbScene &S) {
   S.refl_chain_max = H.refl_chain_max;
   S.n_bvh_nodes = H.nodes.size();
   S.n_tris = H.n_source_tris;
-  S.node_bytes = 64;  // stride; format 2 reads 48 of them per visit
+  S.node_bytes = nfmt >= 3 ? 32 : 64;  // stride; format 2 reads 48 of its 64 per visit
   S.scene_bytes = H.nodes.size() * S.node_bytes + H.tris.size() * (sizeof(Tri) + sizeof(TriUV)) +
                   H.shapes.size() * sizeof(Shape) + d.n_texels * 16;
   return NRB_OK;
@@ -1578,6 +1662,7 @@ int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOp
   S->build_info.build_ms = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   S->build_info.gpu_build_ms = H.gpu_build_ms;
   S->build_info.builder = builder;
+  S->build_info.node_format = (uint32_t)S->view.node_format;
   S->grid_trace = S->sm_count * trace_blocks_per_sm(S->has_shapes);
   S->grid_tail = S->sm_count * (S->has_shapes ? 3 : kTailMinBlocks);
   S->grid_shade = S->sm_count * shade_blocks_per_sm(S->has_shapes);

@@ -21,6 +21,10 @@ namespace nrb {
 //   0 (64 B): n0 = (c0.centre.xyz, c1.centre.x)   n1 = (c1.centre.yz, c0.half.xy)   n2 = (c0.half.z, c1.half.xyz)   n3 as above
 //   2 (48 B used, 64 B stride): (c0.cx, c0.cy, c1.cx, c1.cy) (c0.cz, c1.cz, bf16x2(c0.hx, c0.hy), bf16x2(c1.hx, c1.hy))
 //             (bf16x2(c0.hz, c1.hz), child0, child1, -) (unused); half extents rounded UP to bf16
+//   3 (32 B, 32-byte stride; mesh-only scenes): six words (hi << 16 | lo), one per child and axis — c0.x c0.y c0.z c1.x c1.y c1.z —
+//             then child0, child1.  lo / hi are cells of ONE 16-bit grid over the scene (SceneView.grid_lo / grid_cell), snapped
+//             outward plus one cell, so the record is fetched with one 256-bit load and half the bytes reach the registers.
+//   4         format 3 records walked by the speculative loop (scenes beyond L2)
 // Child code c:  c >= 0 -> inner node index;  c < 0 -> leaf, ~c = (first << 3) | ((count-1) << 1) | is_shape
 //   is_shape = 0: triangles [first, first+count) of the leaf-ordered triangle array (count <= 4)
 //   is_shape = 1: analytic shape `first` of the shape table (count == 1)
@@ -107,8 +111,11 @@ struct Candidate {
 };
 
 struct SceneView {
-  const void *nodes;    // device node records, 64-byte stride
-  int node_format;      // 0: fp32 centres + half extents (64 B read per visit); 2: bf16 half extents (48 B read per visit)
+  const void *nodes;    // device node records: 64-byte stride (formats 0, 2) or 32-byte stride (formats 3, 4)
+  int node_format;      // 0: fp32 centres + half extents (64 B read per visit); 2: bf16 half extents (48 B read per visit);
+                        // 3: child boxes on the scene's 16-bit grid (32 B read per visit); 4: format 3 + speculative loop
+  float grid_lo[3];     // formats 3 / 4: plane coordinate = grid_lo + q * grid_cell, q in [0, 65535]
+  float grid_cell[3];
   const Tri *tris;
   const TriUV *tri_uvs;
   const Shape *shapes;

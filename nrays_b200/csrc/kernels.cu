@@ -103,7 +103,17 @@ struct Hit {
 //             < 0.8 % of its half extent), fetched with one 256-bit + one 128-bit load and unpacked with 6 shifts / masks.
 //             Fewer bytes per visit pay when rays diverge and every lane fetches its own line (C4 hairball: 8.28 ms vs
 //             8.91 ms).  The record keeps its 64-byte stride so a divergent lane still touches ONE cache line per visit.
-// Both run the slab test on the packed FP32 pipe form (FFMA2, PTX fma.rn.f32x2) where it is free: measured on B200 the
+//   format 3: 32 bytes, ONE 256-bit load: the twelve planes are 16-bit cells of one grid over the whole scene (api.cu:
+//             to_device_nodes).  What limits format 0 on B200 is the L1 data stage, which hands 128 bytes per clock to the
+//             register file whether or not the lanes agree on the address: 64 bytes x 32 lanes = 16 clocks per warp and
+//             visit (ncu: 128 M of the 163 M data-stage wavefronts of the primary trace launch of C3 are node records, the
+//             tag stage sees only 21 M).  Half the bytes per visit is half that time.  A cell becomes a float with one PRMT
+//             (0x4B00 in front of it: 2^23 + q) whose selector picks the near or the far plane for this ray's sign, so the
+//             slab test is 12 PRMT + 6 FFMA2 + 8 min/max and needs no centre / half-extent form; the 2^23 is folded into
+//             the ray's constant, which costs half a cell of rounding — the cells are snapped outward by a whole one.
+//             Mesh-only scenes (analytic shapes may have unbounded boxes).  Format 4 = the same records under the
+//             speculative loop.
+// Formats 0 and 2 run the slab test on the packed FP32 pipe form (FFMA2, PTX fma.rn.f32x2) where it is free: measured on B200 the
 // FFMA2 issues at half the FFMA rate (1.86 vs 3.88 warp-instructions / clk / SM, scripts/ubench_ffma2.cu), so it saves issue
 // slots but no FMA-pipe time, and on this loop it is neutral (format 1 = format 0 with FFMA2: 2.37 vs 2.34 ms on C3).
 // Format 0 therefore keeps the scalar FFMA form of round 1; format 2 uses FFMA2 (its operands arrive as pairs anyway).
@@ -120,6 +130,17 @@ NRB_DI u64 fma2(u64 a, u64 b, u64 c) {  // FFMA2: two fp32 FMAs in one issue slo
   return d;
 }
 
+// Triangle fetch of the leaf test (48-byte Woop-free record: v0, e1, e2).
+NRB_DI float4 ld_tri(const float4 *p) {
+#ifdef NRB_TRI_NOALLOC  // experiment: triangles bypass L1 (used once per ray) so nodes and stacks keep it
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+#else
+  return __ldg(p);
+#endif
+}
+
 template <int FMT>
 struct NodeRec;
 template <>
@@ -134,8 +155,17 @@ struct NodeRec<2> {
   int c0, c1;
 };
 
-template <int FMT>
-NRB_DI NodeRec<FMT> load_node(const SceneView &sc, int node);
+template <>
+struct NodeRec<3> {
+  uint32_t w[6];  // (hi << 16 | lo) cells: c0.x c0.y c0.z c1.x c1.y c1.z
+  int c0, c1;
+};
+// FMT -> record layout / loop form
+constexpr int node_layout(int fmt) { return fmt == 4 ? 3 : fmt; }
+constexpr bool speculative_loop(int fmt) { return fmt == 2 || fmt == 4; }
+
+template <int LAYOUT>
+NRB_DI NodeRec<LAYOUT> load_node(const SceneView &sc, int node);
 
 template <>
 NRB_DI NodeRec<0> load_node<0>(const SceneView &sc, int node) {
@@ -163,14 +193,27 @@ NRB_DI NodeRec<2> load_node<2>(const SceneView &sc, int node) {
   asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.cxy0), "=l"(r.cxy1), "=l"(r.cz01), "=l"(hw) : "l"(na));
   asm volatile("ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(wz), "=r"(r.c0), "=r"(r.c1), "=r"(pad) : "l"(na + 32));
   wxy0 = (uint32_t)hw, wxy1 = (uint32_t)(hw >> 32);
-  // bf16 pairs -> fp32 pairs: low half << 16, high half masked
-  r.hxy0 = pk2(__uint_as_float(wxy0 << 16), __uint_as_float(wxy0 & 0xFFFF0000u));
-  r.hxy1 = pk2(__uint_as_float(wxy1 << 16), __uint_as_float(wxy1 & 0xFFFF0000u));
-  r.hz01 = pk2(__uint_as_float(wz << 16), __uint_as_float(wz & 0xFFFF0000u));
+  // bf16 pairs -> fp32 pairs.  Low half: << 16, written as a multiply so it issues on the FMA pipe (IMAD) — the ALU pipe
+  // (min / max, compares, selects: half rate) is the busier one in this loop.  High half: the word as it is; the low half's
+  // bits land in the mantissa tail and make the half extent up to 2^-7 larger — the box only grows.
+  r.hxy0 = pk2(__uint_as_float(wxy0 * 65536u), __uint_as_float(wxy0));
+  r.hxy1 = pk2(__uint_as_float(wxy1 * 65536u), __uint_as_float(wxy1));
+  r.hz01 = pk2(__uint_as_float(wz * 65536u), __uint_as_float(wz));
+  return r;
+}
+
+template <>
+NRB_DI NodeRec<3> load_node<3>(const SceneView &sc, int node) {
+  NodeRec<3> r;
+  const char *na = reinterpret_cast<const char *>(sc.nodes) + (size_t)(unsigned)node * 32u;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.c0), "=r"(r.c1)
+               : "l"(na));
   return r;
 }
 
 // Per-ray constants of the slab test: t(plane) = plane * (1/d) - o * (1/d).
+// Grid form (node layout 3): t(cell q) = (2^23 + q) * idx + oodx with idx = cell / d and oodx = (grid_lo - o) / d - 2^23 * idx.
 struct RayPre {
   float idx, idy, idz, oodx, oody, oodz;
 };
@@ -184,10 +227,49 @@ NRB_DI RayPre ray_pre(V3 o, V3 d) {
   return p;
 }
 
+template <int LAYOUT>
+NRB_DI RayPre ray_pre_for(const SceneView &sc, V3 o, V3 d) {
+  if (LAYOUT != 3) return ray_pre(o, d);
+  const float ooeps = 1.0e-24f;
+  const float ix = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+  const float iy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+  const float iz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+  RayPre p;
+  p.idx = sc.grid_cell[0] * ix, p.idy = sc.grid_cell[1] * iy, p.idz = sc.grid_cell[2] * iz;
+  p.oodx = fmaf(-8388608.0f, p.idx, (sc.grid_lo[0] - o.x) * ix);
+  p.oody = fmaf(-8388608.0f, p.idy, (sc.grid_lo[1] - o.y) * iy);
+  p.oodz = fmaf(-8388608.0f, p.idz, (sc.grid_lo[2] - o.z) * iz);
+  return p;
+}
+
+// What a node visit needs besides RayPre: nothing for the float layouts; for the grid layout the PRMT selectors that turn
+// one half of a (hi << 16 | lo) word into 2^23 + q — the near plane is `lo` where the ray runs in +axis direction.
+template <int LAYOUT>
+struct RayAux {};
+template <>
+struct RayAux<3> {
+  uint32_t nx, ny, nz, fx, fy, fz;  // near / far plane selectors
+};
+template <int LAYOUT>
+NRB_DI RayAux<LAYOUT> ray_aux(const RayPre &) {
+  return RayAux<LAYOUT>();
+}
+template <>
+NRB_DI RayAux<3> ray_aux<3>(const RayPre &p) {
+  RayAux<3> a;  // __byte_perm(word, 0x4B000000, s): 0x7410 -> 0x4B00'lo, 0x7432 -> 0x4B00'hi
+  a.nx = p.idx < 0.0f ? 0x7432u : 0x7410u;
+  a.ny = p.idy < 0.0f ? 0x7432u : 0x7410u;
+  a.nz = p.idz < 0.0f ? 0x7432u : 0x7410u;
+  a.fx = a.nx ^ 0x22u, a.fy = a.ny ^ 0x22u, a.fz = a.nz ^ 0x22u;
+  // opaque to the optimiser: otherwise it re-derives the six selectors from the signs at EVERY visit (3 FSETP + 3 SEL + 3 LOP3)
+  asm volatile("" : "+r"(a.nx), "+r"(a.ny), "+r"(a.nz), "+r"(a.fx), "+r"(a.fy), "+r"(a.fz));
+  return a;
+}
+
 // Both children's slab tests in centre / half-extent form: t(centre) -+ half * |1/d| — 9 FFMA + 4
 // min/max per box and no lo/hi sort (the FMNMX pipe, not the FMA pipe, limits the classic form).
-NRB_DI void test_children(const NodeRec<0> &n, const RayPre &p, float tbest, float &c0min, float &c0max, float &c1min,
-                          float &c1max) {
+NRB_DI void test_children(const NodeRec<0> &n, const RayPre &p, const RayAux<0> &, float tbest, float &c0min, float &c0max,
+                          float &c1min, float &c1max) {
   const float aidx = fabsf(p.idx), aidy = fabsf(p.idy), aidz = fabsf(p.idz);
   float c0tx = fmaf(n.n0.x, p.idx, -p.oodx), c0ty = fmaf(n.n0.y, p.idy, -p.oody), c0tz = fmaf(n.n0.z, p.idz, -p.oodz);
   float c1tx = fmaf(n.n0.w, p.idx, -p.oodx), c1ty = fmaf(n.n1.x, p.idy, -p.oody), c1tz = fmaf(n.n1.y, p.idz, -p.oodz);
@@ -198,8 +280,8 @@ NRB_DI void test_children(const NodeRec<0> &n, const RayPre &p, float tbest, flo
 }
 // The same test on pairs: 9 FFMA2 + 8 min/max.  ptxas folds the |1/d| and -|1/d| operands into FFMA2's abs / neg modifiers
 // and the (1/d.z, 1/d.z) pair into its scalar-broadcast operand form, so the ray constants stay in six registers.
-NRB_DI void test_children(const NodeRec<2> &n, const RayPre &p, float tbest, float &c0min, float &c0max, float &c1min,
-                          float &c1max) {
+NRB_DI void test_children(const NodeRec<2> &n, const RayPre &p, const RayAux<2> &, float tbest, float &c0min, float &c0max,
+                          float &c1min, float &c1max) {
   const u64 idxy = pk2(p.idx, p.idy), idzz = pk2(p.idz, p.idz);
   const u64 noodxy = pk2(-p.oodx, -p.oody), noodzz = pk2(-p.oodz, -p.oodz);
   const u64 aidxy = pk2(fabsf(p.idx), fabsf(p.idy)), aidzz = pk2(fabsf(p.idz), fabsf(p.idz));
@@ -216,6 +298,27 @@ NRB_DI void test_children(const NodeRec<2> &n, const RayPre &p, float tbest, flo
   c0max = fminf(fminf(h0x, h0y), fminf(h0z, tbest));
   c1min = fmaxf(fmaxf(l1x, l1y), fmaxf(l1z, 0.0f));
   c1max = fminf(fminf(h1x, h1y), fminf(h1z, tbest));
+}
+
+// Grid layout: t = (2^23 + q) * s + k per plane; the planes arrive sorted (near, far), so no lo/hi min/max.  x and y run as
+// pairs on FFMA2 with the ray's (s.x, s.y) / (k.x, k.y) register pairs, z on scalar FFMA — no duplicated constants.
+NRB_DI void test_children(const NodeRec<3> &n, const RayPre &p, const RayAux<3> &a, float tbest, float &c0min, float &c0max,
+                          float &c1min, float &c1max) {
+  const uint32_t magic = 0x4B000000u;
+  const u64 sxy = pk2(p.idx, p.idy), kxy = pk2(p.oodx, p.oody);
+#define NRB_Q(w, sel) __uint_as_float(__byte_perm(w, magic, sel))
+  float n0x, n0y, f0x, f0y, n1x, n1y, f1x, f1y;
+  upk2(fma2(pk2(NRB_Q(n.w[0], a.nx), NRB_Q(n.w[1], a.ny)), sxy, kxy), n0x, n0y);
+  upk2(fma2(pk2(NRB_Q(n.w[0], a.fx), NRB_Q(n.w[1], a.fy)), sxy, kxy), f0x, f0y);
+  upk2(fma2(pk2(NRB_Q(n.w[3], a.nx), NRB_Q(n.w[4], a.ny)), sxy, kxy), n1x, n1y);
+  upk2(fma2(pk2(NRB_Q(n.w[3], a.fx), NRB_Q(n.w[4], a.fy)), sxy, kxy), f1x, f1y);
+  const float n0z = fmaf(NRB_Q(n.w[2], a.nz), p.idz, p.oodz), f0z = fmaf(NRB_Q(n.w[2], a.fz), p.idz, p.oodz);
+  const float n1z = fmaf(NRB_Q(n.w[5], a.nz), p.idz, p.oodz), f1z = fmaf(NRB_Q(n.w[5], a.fz), p.idz, p.oodz);
+#undef NRB_Q
+  c0min = fmaxf(fmaxf(n0x, n0y), fmaxf(n0z, 0.0f));
+  c0max = fminf(fminf(f0x, f0y), fminf(f0z, tbest));
+  c1min = fmaxf(fmaxf(n1x, n1y), fmaxf(n1z, 0.0f));
+  c1max = fminf(fminf(f1x, f1y), fminf(f1z, tbest));
 }
 
 // Slab test of one padded box [lo, hi] against the segment [0, tmax] with the ray's precomputed reciprocals — the
@@ -238,7 +341,9 @@ NRB_DI bool traverse(const SceneView &sc, int root, V3 o, V3 d, float tmax, Hit 
   stack[0] = kEmpty;
   int node = root;
   bool found = false;
-  const RayPre pre = ray_pre(o, d);
+  constexpr int L = node_layout(FMT);
+  const RayPre pre = ray_pre_for<L>(sc, o, d);
+  const RayAux<L> aux = ray_aux<L>(pre);
   float tbest = tmax;
 #ifdef NRB_COUNT_VISITS
   unsigned dbg_n = 0, dbg_t = 0;
@@ -250,9 +355,9 @@ NRB_DI bool traverse(const SceneView &sc, int root, V3 o, V3 d, float tmax, Hit 
 #ifdef NRB_COUNT_VISITS
       ++dbg_n;
 #endif
-      const NodeRec<FMT> n = load_node<FMT>(sc, node);
+      const NodeRec<L> n = load_node<L>(sc, node);
       float c0min, c0max, c1min, c1max;
-      test_children(n, pre, tbest, c0min, c0max, c1min, c1max);
+      test_children(n, pre, aux, tbest, c0min, c0max, c1min, c1max);
       bool h0 = c0max >= c0min, h1 = c1max >= c1min;
       if (!h0 && !h1) {
         node = stack[sp--];
@@ -286,7 +391,7 @@ NRB_DI bool traverse(const SceneView &sc, int root, V3 o, V3 d, float tmax, Hit 
 #ifdef NRB_COUNT_VISITS
           ++dbg_t;
 #endif
-          float4 t0 = __ldg(tp + 3 * k), t1 = __ldg(tp + 3 * k + 1), t2 = __ldg(tp + 3 * k + 2);
+          float4 t0 = ld_tri(tp + 3 * k), t1 = ld_tri(tp + 3 * k + 1), t2 = ld_tri(tp + 3 * k + 2);
           float toi, bv, bw;
           if (cast_tri<ANY>(mk(t0.x, t0.y, t0.z), mk(t1.x, t1.y, t1.z), mk(t2.x, t2.y, t2.z), o, d, tbest, toi, bv, bw)) {
             tbest = toi;
@@ -364,7 +469,7 @@ NRB_DI bool trav_leaf(const SceneView &sc, int leaf, int *lm, bool any, float &t
   } else {
     const float4 *tp = reinterpret_cast<const float4 *>(sc.tris + first);
     for (uint32_t k = 0; k < cnt && !hit_any; ++k) {
-      float4 t0 = __ldg(tp + 3 * k), t1 = __ldg(tp + 3 * k + 1), t2 = __ldg(tp + 3 * k + 2);
+      float4 t0 = ld_tri(tp + 3 * k), t1 = ld_tri(tp + 3 * k + 1), t2 = ld_tri(tp + 3 * k + 2);
       float toi, bv, bw;
       if (cast_tri_rt(mk(t0.x, t0.y, t0.z), mk(t1.x, t1.y, t1.z), mk(t2.x, t2.y, t2.z), o, d, tbest, any, toi, bv, bw)) {
         tbest = toi;
@@ -377,11 +482,11 @@ NRB_DI bool trav_leaf(const SceneView &sc, int leaf, int *lm, bool any, float &t
 }
 
 // One node visit: both children tested, the nearer one entered, the farther one pushed.
-template <int FMT>
-NRB_DI void trav_visit(const SceneView &sc, const RayPre &pre, float tbest, int &node, int &sp, int *lm) {
-  const NodeRec<FMT> n = load_node<FMT>(sc, node);
+template <int L>
+NRB_DI void trav_visit(const SceneView &sc, const RayPre &pre, const RayAux<L> &aux, float tbest, int &node, int &sp, int *lm) {
+  const NodeRec<L> n = load_node<L>(sc, node);
   float c0min, c0max, c1min, c1max;
-  test_children(n, pre, tbest, c0min, c0max, c1min, c1max);
+  test_children(n, pre, aux, tbest, c0min, c0max, c1min, c1max);
   bool h0 = c0max >= c0min, h1 = c1max >= c1min;
   if (!h0 && !h1) {
     node = lm[sp--];
@@ -406,11 +511,13 @@ NRB_DI void trav_visit(const SceneView &sc, const RayPre &pre, float tbest, int 
 // sits on one) are tested together.
 template <bool HAS_SHAPES, int FMT>
 NRB_DI void trav_run(const SceneView &sc, LaneTrav &s, int *lm, bool any, int min_active) {
+  constexpr int L = node_layout(FMT);
   int node = s.node, sp = s.sp;
   float tbest = s.tbest;
-  if (FMT != 2) {
+  const RayAux<L> aux = ray_aux<L>(s.pre);
+  if (!speculative_loop(FMT)) {
     while (node != kEmpty) {
-      while ((unsigned)node < (unsigned)kEmpty) trav_visit<FMT>(sc, s.pre, tbest, node, sp, lm);
+      while ((unsigned)node < (unsigned)kEmpty) trav_visit<L>(sc, s.pre, aux, tbest, node, sp, lm);
       while (node < 0) node = trav_leaf<HAS_SHAPES>(sc, node, lm, any, tbest) ? kEmpty : lm[sp--];
       if (__popc(__activemask()) < min_active) break;  // dynamic fetch: let the warp refill its idle lanes
     }
@@ -418,7 +525,7 @@ NRB_DI void trav_run(const SceneView &sc, LaneTrav &s, int *lm, bool any, int mi
     int leaf = s.leaf;  // postponed leaf (< 0) or 0
     while (node != kEmpty || leaf < 0) {
       while ((unsigned)node < (unsigned)kEmpty) {
-        trav_visit<FMT>(sc, s.pre, tbest, node, sp, lm);
+        trav_visit<L>(sc, s.pre, aux, tbest, node, sp, lm);
         if (node < 0 && leaf == 0) {  // first leaf: postpone it and go on with the next node
           leaf = node;
           node = lm[sp--];
@@ -758,7 +865,7 @@ NRB_DI void shadow_query(const SceneView &sc, V3 o, V3 d, float tmax, uint32_t p
 // Shadow-ray state machine.  Phase -1: any-hit under root_opaque.  Phase c >= 0: closest hit
 // of transparent candidate c (its own sub-root), resolved through Material::ambiant.  Returns true if a
 // traversal was started, false if the ray is finished (occluded, or accumulated into its pixel).
-template <bool HAS_SHAPES>
+template <bool HAS_SHAPES, int FMT>
 NRB_DI bool shadow_advance(const SceneView &sc, const ShadowQueue &sq, uint32_t idx, LaneTrav &s, int *lm, int &cand,
                            bool first, bool reverse, float4 *accum) {
   // The transparent filter is folded into the entry's contribution in place (the entry belongs to this lane),
@@ -773,7 +880,7 @@ NRB_DI bool shadow_advance(const SceneView &sc, const ShadowQueue &sq, uint32_t 
     V3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
     if (first && reverse && sc.root_opaque != kEmpty) o = o + d * a.w, d = -d;
     lm_set_ray(lm, o, d);
-    s.pre = ray_pre(o, d);
+    s.pre = ray_pre_for<node_layout(FMT)>(sc, o, d);
   }
   if (first) {
     cand = -1;
@@ -799,7 +906,8 @@ NRB_DI bool shadow_advance(const SceneView &sc, const ShadowQueue &sq, uint32_t 
     const float tmax = sq.a[idx].w;
     for (++cand; cand < sc.n_candidates; ++cand) {
       const Candidate cd = sc.candidates[cand];
-      if (!box_hit(s.pre, cd.lo, cd.hi, tmax)) continue;  // bv cost of the candidate's box
+      // bv cost of the candidate's box (float planes: the grid layout's s.pre is in cells)
+      if (!box_hit(node_layout(FMT) == 3 ? ray_pre(lm_vec(lm, kLmO), lm_vec(lm, kLmD)) : s.pre, cd.lo, cd.hi, tmax)) continue;
       trav_start(s, lm, cd.root, nextafterf(tmax, 3.402823466e+38f));  // closest hit with toi <= tmax
       return true;
     }
@@ -849,7 +957,7 @@ NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *acc
         const float4 a = sq.a[idx], b = sq.b[idx];
         occluded = shadow_planes(sc, sq, idx, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), a.w);
       }
-      active = !occluded && shadow_advance<HAS_SHAPES>(sc, sq, idx, s, lm, cand, true, reverse, accum);
+      active = !occluded && shadow_advance<HAS_SHAPES, FMT>(sc, sq, idx, s, lm, cand, true, reverse, accum);
     }
     if (__ballot_sync(0xFFFFFFFFu, active) == 0u) {
       if (pool_empty(pool)) break;
@@ -857,7 +965,7 @@ NRB_DI void drain_shadow(const SceneView &sc, const ShadowQueue &sq, float4 *acc
     }
     if (active) {
       trav_run<HAS_SHAPES, FMT>(sc, s, lm, cand < 0, min_active);
-      if (s.node == kEmpty) active = shadow_advance<HAS_SHAPES>(sc, sq, idx, s, lm, cand, false, reverse, accum);
+      if (s.node == kEmpty) active = shadow_advance<HAS_SHAPES, FMT>(sc, sq, idx, s, lm, cand, false, reverse, accum);
     }
   }
 }
@@ -890,7 +998,7 @@ NRB_DI void drain_closest(const SceneView &sc, const FrameParams &fp, const RayQ
         hits[idx] = make_float4(0.0f, __uint_as_float(kSkip), 0.0f, 0.0f);
       } else {
         lm_set_ray(lm, o, d);
-        s.pre = ray_pre(o, d);
+        s.pre = ray_pre_for<node_layout(FMT)>(sc, o, d);
         trav_start(s, lm, sc.root_all, 3.402823466e+38f);
         if (HAS_SHAPES) {
           // planes have infinite AABBs: always tested, never in the BVH
@@ -1522,16 +1630,22 @@ void launch_trace(const SceneView &sc, bool has_shapes, const FrameParams &fp, b
 #define NRB_LAUNCH_TRACE(HS, PR, FM)                                                                                          \
   trace_kernel<HS, PR, FM><<<grid, kTraceBlock, 0, st>>>(sc, fp, q, hits, wc_closest, slot_lo, n_slots, sq, accum, wc_shadow, \
                                                          opts)
-  const int sel = (has_shapes ? 4 : 0) | (primary ? 2 : 0) | (sc.node_format == 2 ? 1 : 0);
+  // formats 3 / 4 exist for mesh-only scenes (api.cu: upload_scene never picks them when the scene has analytic shapes)
+  const int sel = (has_shapes ? 16 : 0) | (primary ? 8 : 0) | sc.node_format;
   switch (sel) {
     case 0: NRB_LAUNCH_TRACE(false, false, 0); break;
-    case 1: NRB_LAUNCH_TRACE(false, false, 2); break;
-    case 2: NRB_LAUNCH_TRACE(false, true, 0); break;
-    case 3: NRB_LAUNCH_TRACE(false, true, 2); break;
-    case 4: NRB_LAUNCH_TRACE(true, false, 0); break;
-    case 5: NRB_LAUNCH_TRACE(true, false, 2); break;
-    case 6: NRB_LAUNCH_TRACE(true, true, 0); break;
-    default: NRB_LAUNCH_TRACE(true, true, 2); break;
+    case 2: NRB_LAUNCH_TRACE(false, false, 2); break;
+    case 3: NRB_LAUNCH_TRACE(false, false, 3); break;
+    case 4: NRB_LAUNCH_TRACE(false, false, 4); break;
+    case 8: NRB_LAUNCH_TRACE(false, true, 0); break;
+    case 10: NRB_LAUNCH_TRACE(false, true, 2); break;
+    case 11: NRB_LAUNCH_TRACE(false, true, 3); break;
+    case 12: NRB_LAUNCH_TRACE(false, true, 4); break;
+    case 16: NRB_LAUNCH_TRACE(true, false, 0); break;
+    case 18: NRB_LAUNCH_TRACE(true, false, 2); break;
+    case 24: NRB_LAUNCH_TRACE(true, true, 0); break;
+    case 26: NRB_LAUNCH_TRACE(true, true, 2); break;
+    default: break;  // unreachable: upload_scene validates the format
   }
 #undef NRB_LAUNCH_TRACE
 }
@@ -1570,6 +1684,8 @@ void launch_tail(const SceneView &sc, bool has_shapes, const FrameParams &fp, Ra
   if (has_shapes) {
     if (f2) tail_kernel<true, 2><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum, wc_sh);
     else tail_kernel<true, 0><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum, wc_sh);
+  } else if (sc.node_format >= 3) {  // the tail follows single paths: no warp to speculate for, one form for both
+    tail_kernel<false, 3><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum, wc_sh);
   } else {
     if (f2) tail_kernel<false, 2><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum, wc_sh);
     else tail_kernel<false, 0><<<grid, kTraceBlock, 0, st>>>(sc, fp, qin, wc, qspill, sq, ctr, accum, wc_sh);

@@ -9,14 +9,16 @@ constexpr int kTraceBlock = 128;
 #define NRB_FETCH_PACKETS 2
 #endif
 #ifndef NRB_TRACE_MIN_BLOCKS
-#define NRB_TRACE_MIN_BLOCKS 9
+#define NRB_TRACE_MIN_BLOCKS 10
 #endif
 #ifndef NRB_SMALL_QUEUE
 #define NRB_SMALL_QUEUE (3u << 20)
 #endif
 constexpr unsigned kSmallQueue = NRB_SMALL_QUEUE;  // default TraceOpts.small_queue
 constexpr int kFetchPackets = NRB_FETCH_PACKETS;  // 32-ray packets a warp takes per cursor atomic
-constexpr int kTraceMinBlocks = NRB_TRACE_MIN_BLOCKS;  // resident CTAs / SM the trace kernel is compiled for
+constexpr int kTraceMinBlocks = NRB_TRACE_MIN_BLOCKS;  // resident CTAs / SM the trace kernel is compiled for: 10 -> 48 registers, 8 bytes of
+                                                      // spill outside the visit loop; measured 7 / 8 / 9 / 10 / 12 on C3 2.22 / 2.22 / 2.23 /
+                                                      // 2.21 / 2.34 ms, on C4 7.62 / 7.32 / 7.13 / 6.95 / 7.32 ms (profiles/r2_experiments.txt)
 #ifndef NRB_TAIL_MIN_BLOCKS
 #define NRB_TAIL_MIN_BLOCKS 6
 #endif

@@ -483,6 +483,7 @@ def test_tail_spill_bound_with_weak_attenuation(gpu):
 @pytest.mark.parametrize("env", [dict(NRB_TAIL_RAYS=0), dict(NRB_TAIL_RAYS=1 << 30), dict(NRB_SHADOW_CAP=4096),
                                  dict(NRB_BATCH_SLOTS=4096), dict(NRB_BATCH_SLOTS=4096, NRB_SHADOW_CAP=2048, NRB_TAIL_RAYS=64),
                                  dict(NRB_REVERSE_SHADOW=0), dict(NRB_NODE_FORMAT=2), dict(NRB_NODE_FORMAT=2, NRB_REFILL_RAYS=24, NRB_REFILL_SHADOW=24),
+                                 dict(NRB_NODE_FORMAT=3), dict(NRB_NODE_FORMAT=4, NRB_REFILL_RAYS=24, NRB_REFILL_SHADOW=24),
                                  dict(NRB_REFILL_PRIMARY=20, NRB_REFILL_RAYS=24, NRB_REFILL_SHADOW=24),
                                  dict(NRB_REFILL_PRIMARY=31, NRB_REFILL_RAYS=31, NRB_REFILL_SHADOW=31, NRB_TAIL_RAYS=0)])
 def test_driver_paths_give_the_same_image(gpu, env):
@@ -497,28 +498,36 @@ def test_driver_paths_give_the_same_image(gpu, env):
     assert_parity(img, ref, what=str(env), wh=(96, 80), twin=render_both.twin)
 
 
-@pytest.mark.timeout(120)
-def test_node_format_2_and_speculative_loop_on_small_scenes(gpu):
-    """Node format 2 (bf16 half extents, speculative while-while loop) is chosen for scenes beyond L2; forced here on scenes
-    whose traversal STARTS on a leaf (one shape, <= 4 triangles), on the shape zoo and on a mesh: same image as format 0."""
+@pytest.mark.timeout(180)
+def test_node_formats_and_speculative_loop_on_small_scenes(gpu):
+    """The node formats picked for large scenes — 2 (bf16 half extents, speculative while-while loop), 3 (16-bit grid cells,
+    32-byte records) and 4 (grid + speculative loop) — forced on scenes whose traversal STARTS on a leaf (one shape, <= 4
+    triangles), on the shape zoo and on meshes: same image as format 0.  The grid formats exist for mesh-only scenes; the
+    library keeps format 0 elsewhere, which the build info reports."""
     P1 = np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0]], np.float32)
     scenes = [
-        ([node(Ball(1.0), NormalMaterial())], []),
-        ([node(TriMesh(P1, np.array([[0, 1, 2]], np.uint32), None), NormalMaterial())], []),
-        ([node(TriMesh(*quad_mesh(1.0, 1)), phong()), node(Plane((0, 1, 0)), phong(), pos=(0, -1, 0))], [Light((1, 4, -2), 0.0, 1, (1, 1, 1))]),
-        (zoo([phong(), phong(), phong(), phong(), phong()]), [Light((2, 4, -3), 0.0, 1, (1, 1, 1))]),
+        ([node(Ball(1.0), NormalMaterial())], [], False),
+        ([node(TriMesh(P1, np.array([[0, 1, 2]], np.uint32), None), NormalMaterial())], [], True),
+        ([node(TriMesh(*quad_mesh(1.0, 1)), phong()), node(Plane((0, 1, 0)), phong(), pos=(0, -1, 0))], [Light((1, 4, -2), 0.0, 1, (1, 1, 1))], False),
+        (zoo([phong(), phong(), phong(), phong(), phong()]), [Light((2, 4, -3), 0.0, 1, (1, 1, 1))], False),
         ([node(TriMesh(*quad_mesh(1.5, 6, y=0.3)), phong(), alpha=0.5, refr=1.2), node(TriMesh(*quad_mesh(3.0, 5, y=-0.5)), phong(), refl=(0.3, 0.4))],
-         [Light((0.5, 5, -1), 0.3, 4, (1, 1, 1))]),
+         [Light((0.5, 5, -1), 0.3, 4, (1, 1, 1))], True),
+        ([node(TriMesh(*quad_mesh(2.0, 24, y=0.0)), phong(), refl=(0.2, 0.3)), node(TriMesh(*quad_mesh(0.7, 9, y=0.8)), phong(), pos=(0.2, 0, 0.3)),
+          node(TriMesh(*quad_mesh(200.0, 3, y=-0.6)), phong())], [Light((0.5, 5, -1), 0.0, 1, (1, 1, 1)), Light((-3, 2, -2), 0.2, 2, (0.5, 0.5, 0.6))], True),
     ]
-    for k, (nodes, lights) in enumerate(scenes):
-        imgs = []
-        for fmt in (0, 2):
+    for k, (nodes, lights, mesh_only) in enumerate(scenes):
+        base = None
+        for fmt in (0, 2, 3, 4):
             with _Env(NRB_NODE_FORMAT=fmt):
                 img, st, _, _ = render_both(nodes, lights, eye=(0.3, 1.5, -5.0), w=80, h=60, spp=2, window=1.0, seed=k)
-            imgs.append((img, st))
-        d = np.abs(imgs[0][0] - imgs[1][0]).max(axis=1)
-        assert (d > 1e-4).mean() < 5e-3, (k, float((d > 1e-4).mean()))   # identical hits up to exact ties / box rounding
-        assert abs(int(imgs[0][1].rays_total) - int(imgs[1][1].rays_total)) <= max(4, 2e-3 * imgs[0][1].rays_total), k
+                used = Scene(nodes, lights, (1.0, 1.0, 1.0)).build_info().node_format
+            assert used == (fmt if ((mesh_only and k != 1) or fmt in (0, 2)) else 0), (k, fmt, used)   # scene 1 has no inner node: no grid
+            if base is None:
+                base = (img, st)
+                continue
+            d = np.abs(base[0] - img).max(axis=1)
+            assert (d > 1e-4).mean() < 5e-3, (k, fmt, float((d > 1e-4).mean()))   # identical hits up to exact ties / box rounding
+            assert abs(int(base[1].rays_total) - int(st.rays_total)) <= max(4, 2e-3 * base[1].rays_total), (k, fmt)
 
 
 def test_mesh_scene_driver_paths(gpu):
@@ -540,6 +549,27 @@ def test_mesh_scene_driver_paths(gpu):
         np.testing.assert_allclose(img, base, rtol=0, atol=3e-5, err_msg=str(env))
         assert st.as_dict()["rays_total"] == st0.as_dict()["rays_total"], env
     scene.close()
+
+
+@pytest.mark.parametrize("cfg_id,kw", [("C3", dict(target_tris=30000, lod=4)), ("C4", dict(target_tris=40000))])
+def test_node_formats_on_meshes(gpu, cfg_id, kw):
+    """Every node format renders the mesh configs to the same frame (identical hits: the device boxes only ever grow)."""
+    w, h = 160, 90
+    base = None
+    for fmt in (0, 2, 3, 4):
+        with _Env(NRB_NODE_FORMAT=fmt):
+            scene, camd, cfg = configs.build(cfg_id, **kw)
+        assert scene.build_info().node_format == fmt
+        cam = make_camera(w, h, 2, 1.0, camd.eye, camd.projection((w, h)), seed=2)
+        out = np.empty((w * h, 3), np.float32)
+        st = A.NrbStats()
+        _lib.check(gpu.nrb_render(scene.handle, C.byref(cam), out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(st)))
+        scene.close()
+        if base is None:
+            base = (out, st)
+            continue
+        np.testing.assert_allclose(out, base[0], rtol=0, atol=3e-5, err_msg="format %d" % fmt)
+        assert st.as_dict()["rays_total"] == base[1].as_dict()["rays_total"], fmt
 
 
 @pytest.mark.parametrize("builder,code", [("lbvh", 1), ("ploc", 2)])
