@@ -11,7 +11,10 @@
 namespace nrb {
 
 namespace {
-constexpr int kBins = 16;
+#ifndef NRB_BINS
+#define NRB_BINS 16
+#endif
+constexpr int kBins = NRB_BINS;
 float kCostNode = 1.2f;  // relative cost of one two-box node visit vs one triangle test (env NRB_BVH_CNODE)
 int kLeafMax = kMaxLeafTris;  // env NRB_BVH_LEAF (<= kMaxLeafTris)
 constexpr int kForceMedianDepth = 36;
