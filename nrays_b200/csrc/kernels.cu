@@ -482,11 +482,45 @@ NRB_DI bool trav_leaf(const SceneView &sc, int leaf, int *lm, bool any, float &t
 }
 
 // One node visit: both children tested, the nearer one entered, the farther one pushed.
-template <int L>
+// PREDICATED: the push / pop as predicated PTX instead of branches (used under the speculative loop, where it is worth 3 % on
+// C4; under the plain loop it is neutral on C3 and costs 1 % on C5).
+template <int L, bool PREDICATED>
 NRB_DI void trav_visit(const SceneView &sc, const RayPre &pre, const RayAux<L> &aux, float tbest, int &node, int &sp, int *lm) {
   const NodeRec<L> n = load_node<L>(sc, node);
   float c0min, c0max, c1min, c1max;
   test_children(n, pre, aux, tbest, c0min, c0max, c1min, c1max);
+  if (PREDICATED) {
+    // lm[sp] is the pop source when neither child is hit and — after the increment — the push target when both are, so one
+    // address serves both.
+    const size_t lml = __cvta_generic_to_local(lm);
+    asm volatile(
+        "{\n"
+        " .reg .pred h0, h1, sw, both, none, t1, nh0;\n"
+        " .reg .b32 nearc, farc;\n"
+        " .reg .b64 ad;\n"
+        " setp.ge.f32 h0, %3, %2;\n"
+        " setp.ge.f32 h1, %5, %4;\n"
+        " setp.lt.f32 sw, %4, %2;\n"
+        " and.pred both, h0, h1;\n"
+        " or.pred none, h0, h1;\n"
+        " not.pred none, none;\n"
+        " not.pred nh0, h0;\n"
+        " and.pred t1, both, sw;\n"
+        " or.pred t1, t1, nh0;\n"
+        " selp.b32 nearc, %7, %6, t1;\n"
+        " selp.b32 farc, %6, %7, t1;\n"
+        " @both add.s32 %1, %1, 1;\n"
+        " mad.wide.s32 ad, %1, 4, %8;\n"
+        " @both st.local.b32 [ad], farc;\n"
+        " @none ld.local.b32 nearc, [ad];\n"
+        " @none add.s32 %1, %1, -1;\n"
+        " mov.b32 %0, nearc;\n"
+        "}"
+        : "=r"(node), "+r"(sp)
+        : "f"(c0min), "f"(c0max), "f"(c1min), "f"(c1max), "r"(n.c0), "r"(n.c1), "l"(lml)
+        : "memory");
+    return;
+  }
   bool h0 = c0max >= c0min, h1 = c1max >= c1min;
   if (!h0 && !h1) {
     node = lm[sp--];
@@ -517,7 +551,7 @@ NRB_DI void trav_run(const SceneView &sc, LaneTrav &s, int *lm, bool any, int mi
   const RayAux<L> aux = ray_aux<L>(s.pre);
   if (!speculative_loop(FMT)) {
     while (node != kEmpty) {
-      while ((unsigned)node < (unsigned)kEmpty) trav_visit<L>(sc, s.pre, aux, tbest, node, sp, lm);
+      while ((unsigned)node < (unsigned)kEmpty) trav_visit<L, false>(sc, s.pre, aux, tbest, node, sp, lm);
       while (node < 0) node = trav_leaf<HAS_SHAPES>(sc, node, lm, any, tbest) ? kEmpty : lm[sp--];
       if (__popc(__activemask()) < min_active) break;  // dynamic fetch: let the warp refill its idle lanes
     }
@@ -525,7 +559,7 @@ NRB_DI void trav_run(const SceneView &sc, LaneTrav &s, int *lm, bool any, int mi
     int leaf = s.leaf;  // postponed leaf (< 0) or 0
     while (node != kEmpty || leaf < 0) {
       while ((unsigned)node < (unsigned)kEmpty) {
-        trav_visit<L>(sc, s.pre, aux, tbest, node, sp, lm);
+        trav_visit<L, true>(sc, s.pre, aux, tbest, node, sp, lm);
         if (node < 0 && leaf == 0) {  // first leaf: postpone it and go on with the next node
           leaf = node;
           node = lm[sp--];
