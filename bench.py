@@ -414,6 +414,7 @@ def measure_config(ctx, cfg_id, steps, warmup):
                 ("each rank's resolve kernel stores its tiles into rank 0's image over NVLink (CUDA IPC) + one 4-byte all-reduce"
                  if peer is not None else "one NCCL all-gather of packed tiles + un-tile")),
             "sharded_frame_equals_single_gpu_frame": verified,
+            "node_format": int(scene.build_info().node_format),   # device node record (include/nrays_b200.h: NrbBuildInfo)
             "rays_per_step": rays_dev / steps,
             "rays_reference_per_step": (counts_all["rays_primary"] + counts_all["rays_reflect"] + counts_all["rays_refract"] +
                                         counts_all["rays_shadow"]) / steps,
