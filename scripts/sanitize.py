@@ -10,8 +10,10 @@ from nrays_b200.loader3d import render_camera  # noqa: E402
 
 for name, kw, res, aa in (("C1", dict(globe_size=(32, 16)), (48, 40), (2, 1.0)), ("C2", dict(globe_size=(32, 16)), (40, 40), (1, 0.0)),
                           ("C3", dict(target_tris=12000, lod=8), (64, 36), (2, 1.0)), ("C4", dict(target_tris=16000), (48, 28), (1, 0.0))):
-  for fmt, builder in (("0", "sah"), ("2", "sah"), ("0", "ploc"), ("2", "lbvh")):
-    os.environ["NRB_NODE_FORMAT"] = fmt      # node format 2 = bf16 half extents + speculative traversal loop
+  for fmt, builder in (("0", "sah"), ("2", "sah"), ("0", "ploc"), ("2", "lbvh"), ("3", "sah"), ("4", "ploc")):
+    if fmt in ("3", "4") and name in ("C1", "C2"):
+        continue                             # grid formats: mesh-only scenes
+    os.environ["NRB_NODE_FORMAT"] = fmt      # 2 = bf16 half extents + speculative loop; 3 / 4 = 16-bit grid records, plain / speculative loop
     os.environ["NRB_BUILDER"] = builder      # device builders (LBVH / PLOC) run their own kernels
     scene, cam, cfg = configs.build(name, **kw)
     for env in ({}, {"NRB_TAIL_RAYS": "0"}, {"NRB_BATCH_SLOTS": "1024", "NRB_SHADOW_CAP": "512"},
