@@ -227,7 +227,7 @@ typedef struct NrbBuildOptions {
   uint32_t _reserved[3];
 } NrbBuildOptions;
 
-/* nrb_scene_create with options.  opts == NULL: defaults, and only then the environment variable NRB_BUILDER=sah|lbvh
+/* nrb_scene_create with options.  opts == NULL: defaults, and only then the environment variable NRB_BUILDER=sah|lbvh|ploc
  * is consulted (experiments); an explicit NrbBuildOptions always wins. */
 int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOptions *opts, NrbScene **out);
 
