@@ -115,6 +115,24 @@ void parallel_for(size_t n, F &&fn) {
   for (auto &t : pool) t.join();
 }
 
+// A few thousand uneven tasks (subtrees): worker threads take them one at a time from a shared counter.
+template <class F>
+void parallel_tasks(size_t n, F &&fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  if (const char *e = getenv("NRB_BVH_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+  if (n < 2 || hw < 2) {
+    for (size_t i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<size_t> next(0);
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < std::min<size_t>(hw, n); ++t)
+    pool.emplace_back([&fn, &next, n]() {
+      for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+    });
+  for (auto &t : pool) t.join();
+}
+
 // Sample slots per batch and shadow-queue entries per wave.  Every batch pays its own launches and the tail of each persistent
 // kernel (its slowest warps), so frames larger than one batch want big batches: C5 (132.7 M slots) 30.3 ms at 8 Mi slots,
 // 28.9 at 16 Mi, 28.4 at 32 Mi, 28.2 at 64 Mi; C4 (16.6 M slots) 8.27 -> 7.90 ms once it is one batch.  32 Mi slots cost
@@ -514,6 +532,7 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
   // builds one tree over a set of triangles with the selected builder and appends it to the shared pools
   auto build_set = [&](std::vector<BuildItem> &items, Box *rb, int *code) -> int {
     if (builder == NRB_BUILDER_LBVH || builder == NRB_BUILDER_PLOC) {
+      PhaseTimer sub_pt;
       std::vector<Box> boxes(items.size());
       parallel_for(items.size(), [&](size_t lo_t, size_t hi_t) {
         for (size_t k = lo_t; k < hi_t; ++k) boxes[k] = items[k].box;
@@ -526,6 +545,7 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
                           ? ploc_build(boxes.data(), (uint32_t)boxes.size(), (int)env_size("NRB_PLOC_RADIUS", 16), sub, order, &root, rb, &depth, &ms)
                           : lbvh_build(boxes.data(), (uint32_t)boxes.size(), sub, order, &root, rb, &depth, &ms);
       if (e != cudaSuccess) return fail(NRB_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString(e));
+      sub_pt.lap("  boxes + device build call");
       H.gpu_build_ms += ms;
       const int node_off = (int)bb.nodes.size();
       const uint32_t tri_off = (uint32_t)bb.tri_order.size();
@@ -534,20 +554,26 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
         uint32_t lc = (uint32_t)~c;
         return ~(int)((((lc >> 3) + tri_off) << 3) | (lc & 7u));
       };
-      bb.nodes.resize((size_t)node_off + sub.size());
-      parallel_for(sub.size(), [&](size_t lo_t, size_t hi_t) {
-        for (size_t k = lo_t; k < hi_t; ++k) {
-          BvhNode nd = sub[k];
-          nd.n3.x = shift(nd.n3.x);
-          nd.n3.y = shift(nd.n3.y);
-          bb.nodes[(size_t)node_off + k] = nd;
-        }
-      });
+      const size_t n_sub = sub.size();
+      if (node_off == 0 && tri_off == 0) {
+        bb.nodes = std::move(sub);  // first tree of the pool: the downloaded nodes ARE the pool (no 100 MB copy, no zero fill)
+      } else {
+        bb.nodes.resize((size_t)node_off + n_sub);
+        parallel_for(n_sub, [&](size_t lo_t, size_t hi_t) {
+          for (size_t k = lo_t; k < hi_t; ++k) {
+            BvhNode nd = sub[k];
+            nd.n3.x = shift(nd.n3.x);
+            nd.n3.y = shift(nd.n3.y);
+            bb.nodes[(size_t)node_off + k] = nd;
+          }
+        });
+      }
       bb.tri_order.resize((size_t)tri_off + order.size());
       parallel_for(order.size(), [&](size_t lo_t, size_t hi_t) {
         for (size_t k = lo_t; k < hi_t; ++k) bb.tri_order[(size_t)tri_off + k] = (uint32_t)items[order[k]].payload;
       });
       *code = shift(root);
+      sub_pt.lap("  splice into the node pool");
       const int prev_depth = bb.max_depth_seen;
       bb.max_depth_seen = std::max(prev_depth, depth + 1);
       // ---- SAH top ----------------------------------------------------------------------------------------------------
@@ -557,29 +583,46 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
       // its subtrees hold <= T triangles and the host's binned-SAH builder rebuilds everything above the cut over those few
       // thousand subtree boxes (milliseconds).  NRB_RESAH_TOP=0 keeps the device tree as built.
       if (env_size("NRB_RESAH_TOP", 1) != 0 && *code >= 0) {
-        const size_t n_sub = sub.size();
-        // triangles below every spliced node (iterative post-order from the root)
+        // triangles below every spliced node and the levels of inner nodes under it.  The top of the tree is walked breadth-first
+        // until ~2 k subtrees are open; those are finished in parallel (iterative post-order each), then the top bottom-up.
         std::vector<uint32_t> cnt(n_sub, 0);
+        std::vector<uint16_t> dep(n_sub, 0);
         auto leaf_count = [](int c) -> uint32_t { return (((uint32_t)~c >> 1) & 3u) + 1u; };
+        auto finish = [&](int li) {  // li's children are done (or leaves)
+          const BvhNode &nd = bb.nodes[(size_t)node_off + li];
+          const int a = nd.n3.x, b = nd.n3.y;
+          cnt[li] = (a >= 0 ? cnt[a - node_off] : leaf_count(a)) + (b >= 0 ? cnt[b - node_off] : leaf_count(b));
+          dep[li] = (uint16_t)(1 + std::max<int>(a >= 0 ? dep[a - node_off] : 0, b >= 0 ? dep[b - node_off] : 0));
+        };
         {
-          std::vector<std::pair<int, int>> st;  // (local node, state)
-          st.emplace_back(*code - node_off, 0);
-          while (!st.empty()) {
-            auto &top = st.back();
-            const BvhNode &nd = bb.nodes[(size_t)node_off + top.first];
-            if (top.second == 0) {
-              top.second = 1;
-              if (nd.n3.x >= 0) st.emplace_back(nd.n3.x - node_off, 0);
-              if (nd.n3.y >= 0) st.emplace_back(nd.n3.y - node_off, 0);
-            } else {
-              const uint32_t a = nd.n3.x >= 0 ? cnt[nd.n3.x - node_off] : leaf_count(nd.n3.x);
-              const uint32_t b = nd.n3.y >= 0 ? cnt[nd.n3.y - node_off] : leaf_count(nd.n3.y);
-              cnt[top.first] = a + b;
-              st.pop_back();
-            }
+          std::vector<int> top{*code - node_off};  // breadth-first prefix: children always behind their parent
+          size_t head = 0;
+          while (head < top.size() && top.size() - head < 2048) {
+            const BvhNode &nd = bb.nodes[(size_t)node_off + top[head++]];
+            if (nd.n3.x >= 0) top.push_back(nd.n3.x - node_off);
+            if (nd.n3.y >= 0) top.push_back(nd.n3.y - node_off);
           }
+          parallel_tasks(top.size() - head, [&](size_t r) {
+            std::vector<std::pair<int, int>> st;  // (local node, state)
+            st.emplace_back(top[head + r], 0);
+            while (!st.empty()) {
+              auto &t = st.back();
+              if (t.second == 0) {
+                t.second = 1;
+                const BvhNode &nd = bb.nodes[(size_t)node_off + t.first];
+                const int a = nd.n3.x, b = nd.n3.y;  // (t is invalidated by the pushes)
+                if (a >= 0) st.emplace_back(a - node_off, 0);
+                if (b >= 0) st.emplace_back(b - node_off, 0);
+              } else {
+                finish(t.first);
+                st.pop_back();
+              }
+            }
+          });
+          for (size_t k = head; k-- > 0;) finish(top[k]);
         }
         const uint32_t total = cnt[*code - node_off];
+        sub_pt.lap("  subtree triangle counts");
         // cut size: ~65 k subtrees for meshes up to 1 M triangles, ~33 k beyond (C3: T = 4 -> 2.39 ms against 2.23 for the host
         // SAH tree, 2.94 as built; C4: T = 88 -> 7.75 ms against 7.28, 8.02 as built; the SAH top costs 30-150 ms of host time)
         const uint32_t T = (uint32_t)env_size("NRB_RESAH_LEAF", std::max<size_t>(4, total / (total <= (1u << 20) ? 65536u : 32768u)));
@@ -600,7 +643,9 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
               else cut.push_back(BuildItem{*bx[k], ch[k]});
             }
           }
+          sub_pt.lap("  cut");
           *code = bb.build_payloads(cut, rb);
+          sub_pt.lap("  SAH top");
           // true depth of the rebuilt tree (levels of inner nodes on the longest path): SAH top + the device subtree below it
           int deepest = 0;
           std::vector<std::pair<int, int>> st{{*code, 1}};
@@ -608,12 +653,17 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
             const auto [c, lvl] = st.back();
             st.pop_back();
             if (c < 0) continue;
+            if ((size_t)c < (size_t)node_off + n_sub) {  // a cut subtree (device-built, untouched)
+              deepest = std::max(deepest, lvl - 1 + (int)dep[c - node_off]);
+              continue;
+            }
             deepest = std::max(deepest, lvl);
             const BvhNode &nd = bb.nodes[(size_t)c];
             st.emplace_back(nd.n3.x, lvl + 1);
             st.emplace_back(nd.n3.y, lvl + 1);
           }
           bb.max_depth_seen = std::max(prev_depth, deepest);
+          sub_pt.lap("  depth of the joined tree");
         }
       }
       return NRB_OK;
@@ -633,6 +683,9 @@ int flatten_scene(const NrbSceneDesc &d, HostScene &H, uint32_t builder = NRB_BU
         for (size_t t = lo_t; t < hi_t; ++t) items[at + t] = BuildItem{tri_box[b0 + t], (int)(b0 + t)};
       });
     }
+    PhaseTimer items_pt;
+    items_pt.on = items_pt.on && !items.empty();
+    items_pt.lap("  build items");
     if (!items.empty()) {
       Box rb;
       int code = kEmpty;

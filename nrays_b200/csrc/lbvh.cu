@@ -297,6 +297,7 @@ cudaError_t lbvh_build(const Box *h_boxes, uint32_t n, std::vector<BvhNode> &nod
   if (gpu_ms) cudaEventElapsedTime(gpu_ms, e0, e1);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  nodes_out.reserve((size_t)n_out + n_out / 8 + 131072);  // room for the trees the caller appends (SAH top, top-level joins): no 100 MB reallocation
   nodes_out.resize(n_out);
   LB_CU(cudaMemcpy(nodes_out.data(), d_out, sizeof(BvhNode) * n_out, cudaMemcpyDeviceToHost));
   LB_CU(cudaMemcpy(order_out.data(), d_vals2, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
@@ -581,6 +582,7 @@ cudaError_t ploc_build(const Box *h_boxes, uint32_t n, int radius, std::vector<B
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   clk.lap("offsets + emit");
+  nodes_out.reserve((size_t)n_out + n_out / 8 + 131072);  // room for the trees the caller appends (SAH top, top-level joins): no 100 MB reallocation
   nodes_out.resize(n_out);
   LB_CU(cudaMemcpy(nodes_out.data(), d_out, sizeof(BvhNode) * n_out, cudaMemcpyDeviceToHost));
   LB_CU(cudaMemcpy(order_out.data(), d_order, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
