@@ -551,6 +551,30 @@ def test_mesh_scene_driver_paths(gpu):
     scene.close()
 
 
+def test_grid_format_needs_a_grid_that_resolves_the_geometry(gpu):
+    """One far-away triangle stretches the 16-bit grid until a cell is larger than the mesh that matters: the library keeps
+    float boxes (format 4 requested -> 2, format 3 -> 0) instead of letting every snapped box overlap its neighbours."""
+    P, I, UV = quad_mesh(1.0, 48, y=0.0)
+    far = np.array([[4.0e5, 0, 4.0e5], [4.0e5 + 1, 0, 4.0e5], [4.0e5, 0, 4.0e5 + 1]], np.float32)
+    P2 = np.concatenate([P, far]).astype(np.float32)
+    I2 = np.concatenate([I, np.array([[len(P), len(P) + 1, len(P) + 2]], np.uint32)]).astype(np.uint32)
+    nodes = [node(TriMesh(P2, I2, None), phong())]
+    lights = [Light((0.5, 5, -1), 0.0, 1, (1, 1, 1))]
+    imgs = {}
+    for fmt, want in ((0, 0), (3, 0), (4, 2)):
+        with _Env(NRB_NODE_FORMAT=fmt):
+            img, st, _, _ = render_both(nodes, lights, eye=(0.3, 1.5, -5.0), w=64, h=48, spp=1, window=0.0, seed=0)
+            assert Scene(nodes, lights, (1.0, 1.0, 1.0)).build_info().node_format == want, fmt
+        imgs[fmt] = img
+    np.testing.assert_allclose(imgs[3], imgs[0], rtol=0, atol=3e-5)
+    np.testing.assert_allclose(imgs[4], imgs[0], rtol=0, atol=3e-5)
+    # ... and with the limit lifted the grid format still renders the same frame (correct, only slow on real scenes)
+    with _Env(NRB_NODE_FORMAT=3, NRB_GRID_MAX_INFLATION=1e30):
+        img, st, _, _ = render_both(nodes, lights, eye=(0.3, 1.5, -5.0), w=64, h=48, spp=1, window=0.0, seed=0)
+        assert Scene(nodes, lights, (1.0, 1.0, 1.0)).build_info().node_format == 3
+    np.testing.assert_allclose(img, imgs[0], rtol=0, atol=3e-5)
+
+
 @pytest.mark.parametrize("cfg_id,kw", [("C3", dict(target_tris=30000, lod=4)), ("C4", dict(target_tris=40000))])
 def test_node_formats_on_meshes(gpu, cfg_id, kw):
     """Every node format renders the mesh configs to the same frame (identical hits: the device boxes only ever grow)."""
