@@ -43,6 +43,21 @@ void pad_box(Box &b, float scene_extent) {
   }
 }
 
+// The top levels of a large tree run on the calling thread while the worker threads have nothing to do yet: their passes over
+// the items (bounds, binning) are split into one contiguous chunk per hardware thread.
+static constexpr size_t kParallelPass = 1u << 18;
+template <class F>
+static void chunked(size_t n, unsigned hw, F &&fn) {  // fn(thread, lo, hi)
+  const size_t chunk = (n + hw - 1) / hw;
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < hw; ++t) {
+    const size_t lo = (size_t)t * chunk, hi = std::min(n, lo + chunk);
+    if (lo >= hi) break;
+    pool.emplace_back([&fn, t, lo, hi]() { fn(t, lo, hi); });
+  }
+  for (auto &th : pool) th.join();
+}
+
 // Placeholder child codes for deferred subtrees: inner-node indices never get this large.
 static constexpr int kPlaceholderBase = 0x40000000;
 
@@ -78,27 +93,47 @@ int BvhBuilder::build_triangles(std::vector<BuildItem> &items, Box *root_box) {
     for (unsigned t = 0; t < std::min<unsigned>(hw, (unsigned)tasks.size()); ++t) pool.emplace_back(worker);
     for (auto &t : pool) t.join();
   }
-  // splice: shift node indices and leaf triangle offsets of each private pool
+  // splice: shift node indices and leaf triangle offsets of each private pool (every pool copied by a worker thread)
   std::vector<int> resolved(tasks.size());
+  std::vector<size_t> node_at(tasks.size() + 1), tri_at(tasks.size() + 1);
+  node_at[0] = nodes.size(), tri_at[0] = tri_order.size();
   for (size_t i = 0; i < tasks.size(); ++i) {
-    const int node_off = (int)nodes.size();
-    const uint32_t tri_off = (uint32_t)tri_order.size();
-    auto shift = [&](int c) -> int {
-      if (c >= 0) return c + node_off;
-      uint32_t code = (uint32_t)~c;
-      uint32_t first = (code >> 3) + tri_off;
-      return ~(int)((first << 3) | (code & 7u));
-    };
-    for (BvhNode n : subs[i].nodes) {
-      n.n3.x = shift(n.n3.x);
-      n.n3.y = shift(n.n3.y);
-      nodes.push_back(n);
-    }
-    tri_order.insert(tri_order.end(), subs[i].tri_order.begin(), subs[i].tri_order.end());
-    resolved[i] = shift(sub_root[i]);
-    max_depth_seen = std::max(max_depth_seen, sub_depth[i]);
-    subs[i] = BvhBuilder();
+    node_at[i + 1] = node_at[i] + subs[i].nodes.size();
+    tri_at[i + 1] = tri_at[i] + subs[i].tri_order.size();
   }
+  nodes.resize(node_at.back());
+  tri_order.resize(tri_at.back());
+  {
+    std::atomic<size_t> next(0);
+    auto worker = [&]() {
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i >= tasks.size()) return;
+        const int node_off = (int)node_at[i];
+        const uint32_t tri_off = (uint32_t)tri_at[i];
+        auto shift = [&](int c) -> int {
+          if (c >= 0) return c + node_off;
+          uint32_t code = (uint32_t)~c;
+          uint32_t first = (code >> 3) + tri_off;
+          return ~(int)((first << 3) | (code & 7u));
+        };
+        BvhNode *dst = nodes.data() + node_at[i];
+        for (size_t k = 0; k < subs[i].nodes.size(); ++k) {
+          BvhNode n = subs[i].nodes[k];
+          n.n3.x = shift(n.n3.x);
+          n.n3.y = shift(n.n3.y);
+          dst[k] = n;
+        }
+        std::copy(subs[i].tri_order.begin(), subs[i].tri_order.end(), tri_order.begin() + (ptrdiff_t)tri_at[i]);
+        resolved[i] = shift(sub_root[i]);
+        subs[i] = BvhBuilder();
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < std::min<unsigned>(hw, (unsigned)tasks.size()); ++t) pool.emplace_back(worker);
+    for (auto &t : pool) t.join();
+  }
+  for (size_t i = 0; i < tasks.size(); ++i) max_depth_seen = std::max(max_depth_seen, sub_depth[i]);
   auto fix = [&](int &c) {
     if (c >= kPlaceholderBase && c != kEmpty) c = resolved[c - kPlaceholderBase];
   };
@@ -119,10 +154,26 @@ int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, B
   Box bounds, cbounds;
   bounds.reset();
   cbounds.reset();
-  for (size_t i = 0; i < n; ++i) {
-    bounds.grow(items[i].box);
-    float c[3] = {centroid(items[i].box, 0), centroid(items[i].box, 1), centroid(items[i].box, 2)};
-    cbounds.grow(c);
+  unsigned hw = 1;
+  if (tasks_ && n >= kParallelPass) {
+    hw = std::max(1u, std::thread::hardware_concurrency());
+    if (const char *e = getenv("NRB_BVH_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+  }
+  auto grow_bounds = [&](size_t lo_i, size_t hi_i, Box &bd, Box &cb) {
+    for (size_t i = lo_i; i < hi_i; ++i) {
+      bd.grow(items[i].box);
+      float c[3] = {centroid(items[i].box, 0), centroid(items[i].box, 1), centroid(items[i].box, 2)};
+      cb.grow(c);
+    }
+  };
+  if (hw > 1) {
+    std::vector<Box> pb(hw), pc(hw);
+    for (unsigned t = 0; t < hw; ++t) pb[t].reset(), pc[t].reset();
+    chunked(n, hw, [&](unsigned t, size_t lo_i, size_t hi_i) { grow_bounds(lo_i, hi_i, pb[t], pc[t]); });
+    for (unsigned t = 0; t < hw; ++t)
+      if (pb[t].valid()) bounds.grow(pb[t]), cbounds.grow(pc[t]);
+  } else {
+    grow_bounds(0, n, bounds, cbounds);
   }
   *out_box = bounds;
 
@@ -153,11 +204,28 @@ int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, B
       size_t cnt[kBins];
       for (int b = 0; b < kBins; ++b) bb[b].reset(), cnt[b] = 0;
       float scale = (float)kBins * (1.0f - 1e-6f) / ext;
-      for (size_t i = 0; i < n; ++i) {
-        int b = (int)((centroid(items[i].box, axis) - lo) * scale);
-        b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
-        bb[b].grow(items[i].box);
-        cnt[b]++;
+      auto bin_items = [&](size_t lo_i, size_t hi_i, Box *tb, size_t *tc) {
+        for (size_t i = lo_i; i < hi_i; ++i) {
+          int b = (int)((centroid(items[i].box, axis) - lo) * scale);
+          b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+          tb[b].grow(items[i].box);
+          tc[b]++;
+        }
+      };
+      if (hw > 1) {
+        struct ThreadBins {
+          Box bb[kBins];
+          size_t cnt[kBins];
+        };
+        std::vector<ThreadBins> tb(hw);
+        for (auto &t : tb)
+          for (int b = 0; b < kBins; ++b) t.bb[b].reset(), t.cnt[b] = 0;
+        chunked(n, hw, [&](unsigned t, size_t lo_i, size_t hi_i) { bin_items(lo_i, hi_i, tb[t].bb, tb[t].cnt); });
+        for (auto &t : tb)
+          for (int b = 0; b < kBins; ++b)
+            if (t.cnt[b]) bb[b].grow(t.bb[b]), cnt[b] += t.cnt[b];
+      } else {
+        bin_items(0, n, bb, cnt);
       }
       float right_area[kBins];
       size_t right_cnt[kBins];
