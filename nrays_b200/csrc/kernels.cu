@@ -95,24 +95,25 @@ struct Hit {
   float u, v;
 };
 
-// One node record as the traversal loop sees it (device_types.cuh "node formats").  Two formats are compiled and the scene
-// picks one at creation (api.cu):
+// One node record as the traversal loop sees it (device_types.cuh "node formats").  Three layouts are compiled and the scene
+// picks one at creation (api.cu: upload_scene):
 //   format 0: 64 bytes, two 256-bit loads — the fastest form while the scene lives in L2 and neighbouring rays visit the same
-//             nodes (C3: 2.34 ms vs 2.43 ms for format 2).
+//             nodes (C3: 2.24 ms; format 2 under the same loop 2.3, format 3 2.57).
 //   format 2: 48 bytes used of a 64-byte record: the six half extents are stored as bf16 (rounded up: the box only grows, by
-//             < 0.8 % of its half extent), fetched with one 256-bit + one 128-bit load and unpacked with 6 shifts / masks.
-//             Fewer bytes per visit pay when rays diverge and every lane fetches its own line (C4 hairball: 8.28 ms vs
-//             8.91 ms).  The record keeps its 64-byte stride so a divergent lane still touches ONE cache line per visit.
+//             < 0.8 % of its half extent), fetched with one 256-bit + one 128-bit load.  The record keeps its 64-byte stride so
+//             a divergent lane still touches ONE cache line per visit.  Scenes beyond L2 that have analytic shapes.
 //   format 3: 32 bytes, ONE 256-bit load: the twelve planes are 16-bit cells of one grid over the whole scene (api.cu:
-//             to_device_nodes).  What limits format 0 on B200 is the L1 data stage, which hands 128 bytes per clock to the
-//             register file whether or not the lanes agree on the address: 64 bytes x 32 lanes = 16 clocks per warp and
-//             visit (ncu: 128 M of the 163 M data-stage wavefronts of the primary trace launch of C3 are node records, the
-//             tag stage sees only 21 M).  Half the bytes per visit is half that time.  A cell becomes a float with one PRMT
-//             (0x4B00 in front of it: 2^23 + q) whose selector picks the near or the far plane for this ray's sign, so the
-//             slab test is 12 PRMT + 6 FFMA2 + 8 min/max and needs no centre / half-extent form; the 2^23 is folded into
-//             the ray's constant, which costs half a cell of rounding — the cells are snapped outward by a whole one.
-//             Mesh-only scenes (analytic shapes may have unbounded boxes).  Format 4 = the same records under the
-//             speculative loop.
+//             to_device_nodes).  A cell becomes a float with one PRMT (0x4B00 in front of it: 2^23 + q) whose selector picks the
+//             near or the far plane for this ray's sign, so the slab test is 12 PRMT + 4 FFMA2 + 4 FFMA + 8 min/max and needs
+//             no centre / half-extent form; the 2^23 is folded into the ray's constant, which costs half a cell of rounding —
+//             the cells are snapped outward by a whole one.  Mesh-only scenes (analytic shapes may have unbounded boxes).
+//   format 4: format-3 records under the speculative loop — the choice for mesh-only scenes beyond L2 (C4: 7.14 ms against 7.32
+//             for format 2, with half the node memory).
+// What the formats taught (profiles/README.md): the L1 data stage hands 128 bytes per clock to the register file whether or not
+// the lanes agree on the address (64 bytes x 32 lanes = 16 clocks per warp and visit; ncu: 128 M of the 163 M data-stage
+// wavefronts of the primary launch of C3 are node records), so it reads 85 % busy — yet halving those bytes buys nothing on C3:
+// the loop is bound by instruction issue, and the PRMTs of format 3 land on the ALU pipe (min/max, compares, selects, integer
+// adds), which issues at half rate and is the busiest pipe of the visit.  Fewer bytes pay only where lines miss L1 / L2 (C4).
 // Formats 0 and 2 run the slab test on the packed FP32 pipe form (FFMA2, PTX fma.rn.f32x2) where it is free: measured on B200 the
 // FFMA2 issues at half the FFMA rate (1.86 vs 3.88 warp-instructions / clk / SM, scripts/ubench_ffma2.cu), so it saves issue
 // slots but no FMA-pipe time, and on this loop it is neutral (format 1 = format 0 with FFMA2: 2.37 vs 2.34 ms on C3).
@@ -130,16 +131,9 @@ NRB_DI u64 fma2(u64 a, u64 b, u64 c) {  // FFMA2: two fp32 FMAs in one issue slo
   return d;
 }
 
-// Triangle fetch of the leaf test (48-byte Woop-free record: v0, e1, e2).
-NRB_DI float4 ld_tri(const float4 *p) {
-#ifdef NRB_TRI_NOALLOC  // experiment: triangles bypass L1 (used once per ray) so nodes and stacks keep it
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-#else
-  return __ldg(p);
-#endif
-}
+// Triangle fetch of the leaf test (48-byte record: v0, e1, e2).  Loading with L1::no_allocate — triangles are used once per ray —
+// was measured and dropped (C3 2.26-2.28 vs 2.22 ms, C4 unchanged).
+NRB_DI float4 ld_tri(const float4 *p) { return __ldg(p); }
 
 template <int FMT>
 struct NodeRec;
