@@ -936,8 +936,11 @@ NodeGrid make_node_grid(const std::vector<BvhNode> &in) {
   g.ok = !in.empty();
   for (int k = 0; k < 3; ++k) {
     if (!(lo[k] <= hi[k]) || !(std::fabs(lo[k]) < 1.0e9f) || !(std::fabs(hi[k]) < 1.0e9f)) g.ok = false;
-    const double ext = std::max((double)hi[k] - (double)lo[k], 1.0e-12 + 1.0e-6 * std::max(std::fabs((double)lo[k]), std::fabs((double)hi[k])));
-    g.cell[k] = (float)(ext / (kGridCells - 4.0));  // float rounding of cell / lo must not push a box off the grid
+    // A cell is never finer than four float steps of the coordinates themselves (flat axes, scenes far from the origin): the one
+    // cell of margin then covers at least what format 0's ulp-scaled padding covers.  (The "- 4": float rounding of cell / lo
+    // must not push a box off the grid.)
+    const double mag = std::max(std::fabs((double)lo[k]), std::fabs((double)hi[k]));
+    g.cell[k] = (float)std::max({((double)hi[k] - (double)lo[k]) / (kGridCells - 4.0), mag * 4.8e-7, 1.0e-20});
     g.lo[k] = (float)((double)lo[k] - (kGridMargin + 2.0) * (double)g.cell[k]);
   }
   return g;

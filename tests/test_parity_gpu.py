@@ -575,6 +575,26 @@ def test_grid_format_needs_a_grid_that_resolves_the_geometry(gpu):
     np.testing.assert_allclose(img, imgs[0], rtol=0, atol=3e-5)
 
 
+def test_grid_format_far_from_the_origin(gpu):
+    """A mesh 2000 units from the origin, 2 units wide: the grid cell is floored at four float steps of the coordinates, so the
+    one cell of margin still covers the f32 rounding of the slab test: same frame and ray counts as format 0."""
+    off = np.array([1000.0, 500.0, -2000.0])
+    nodes = [node(TriMesh(*quad_mesh(1.0, 24, y=0.0)), phong(), pos=tuple(off), refl=(0.3, 0.4)),
+             node(TriMesh(*quad_mesh(0.4, 6, y=0.5)), phong(), pos=tuple(off + (0.1, 0.0, 0.2)))]
+    lights = [Light(tuple(off + (0.5, 5.0, -1.0)), 0.0, 1, (1, 1, 1))]
+    eye = tuple(off + (0.3, 1.5, -5.0))
+    imgs = {}
+    for fmt in (0, 3, 4):
+        with _Env(NRB_NODE_FORMAT=fmt):
+            img, st, ref, ost = render_both(nodes, lights, eye=eye, at=tuple(off), w=96, h=64, spp=2, window=1.0, seed=4)
+            assert Scene(nodes, lights, (1.0, 1.0, 1.0)).build_info().node_format == fmt
+        imgs[fmt] = (img, st)
+    assert imgs[0][1].rays_shadow > 0 and imgs[0][1].rays_reflect > 0
+    for fmt in (3, 4):
+        np.testing.assert_allclose(imgs[fmt][0], imgs[0][0], rtol=0, atol=3e-5)
+        assert imgs[fmt][1].rays_total == imgs[0][1].rays_total
+
+
 @pytest.mark.parametrize("cfg_id,kw", [("C3", dict(target_tris=30000, lod=4)), ("C4", dict(target_tris=40000))])
 def test_node_formats_on_meshes(gpu, cfg_id, kw):
     """Every node format renders the mesh configs to the same frame (identical hits: the device boxes only ever grow)."""
