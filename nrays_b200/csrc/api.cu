@@ -1354,7 +1354,6 @@ int render_device(NrbScene &S, const NrbCamera &cam, const NrbTileSet *tiles, fl
   CU(cudaMemsetAsync(dc, 0, sizeof(Counters), st));
 
   const uint32_t per_tile = NRB_TILE * NRB_TILE * fp.spp;
-  const uint64_t total_slots = (uint64_t)fp.n_local_tiles * per_tile;
   const uint64_t batch_slots_req = env_size("NRB_BATCH_SLOTS", kBatchSlots);
   const uint32_t tiles_per_batch = (uint32_t)std::max<uint64_t>(1, batch_slots_req / per_tile);
   const uint64_t shadow_cap_req = env_size("NRB_SHADOW_CAP", kShadowCap);
@@ -1712,7 +1711,7 @@ int nrb_scene_create(const NrbSceneDesc *desc, int device, NrbScene **out) {
 
 int nrb_scene_create_opts(const NrbSceneDesc *desc, int device, const NrbBuildOptions *opts, NrbScene **out) {
   if (!desc || !out) return fail(NRB_ERR_INVALID_ARG, "desc/out is NULL");
-  uint32_t builder = opts ? opts->builder : NRB_BUILDER_SAH;
+  uint32_t builder = opts ? opts->builder : (uint32_t)NRB_BUILDER_SAH;
   if (!opts) {  // the environment only fills in for a caller that expressed no choice
     if (const char *e = getenv("NRB_BUILDER"))
       builder = (std::string(e) == "lbvh") ? NRB_BUILDER_LBVH : (std::string(e) == "ploc") ? NRB_BUILDER_PLOC : NRB_BUILDER_SAH;
