@@ -24,7 +24,10 @@ constexpr int kTraceMinBlocks = NRB_TRACE_MIN_BLOCKS;  // resident CTAs / SM the
 #endif
 constexpr int kTailMinBlocks = NRB_TAIL_MIN_BLOCKS;  // resident CTAs / SM of the tail kernel (mesh-only scenes): 6 -> 80 registers with ~200 B of
                                                    // spills beats 4 (114 registers, no spills) by 2.5 % of the C3 frame: the chains are latency-bound
-constexpr int kShadeBlock = 128;
+#ifndef NRB_SHADE_BLOCK
+#define NRB_SHADE_BLOCK 128
+#endif
+constexpr int kShadeBlock = NRB_SHADE_BLOCK;  // >= 64 (two reservation leaders)
 #ifndef NRB_SHADE_MIN_BLOCKS
 #define NRB_SHADE_MIN_BLOCKS 6
 #endif
