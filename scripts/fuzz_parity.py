@@ -5,7 +5,8 @@ on the device through the C-ABI under random driver / kernel knobs and compared 
     python scripts/fuzz_parity.py [n_scenes] [seed]
 
 Prints one line per scene and a summary; exits 1 if any scene is outside the stated tolerance
-(per-channel |delta| <= 1/255 on >= 99.5 % of the pixels of these tiny images, ray counts within 0.5 %).
+(per-channel |delta| <= 1/255 on >= 99.5 % of the pixels of these tiny images, ray counts within 0.5 %) without a proof that it
+is precision-chaotic (the same proof tests/test_fuzz_gpu.py demands of its fixed-seed slice).
 A scene that fails against the f64 oracle is re-checked against the oracle's f32 mode.  Scenes with deep mirror + glass
 recursion (max_depth 12, both children at every hit) have chaotic path trees: one branch flipped by rounding changes the
 ray count by thousands while the image stays within tolerance — the f64 and f32 oracles disagree with each other
@@ -141,6 +142,24 @@ def main():
             if m32["frac_over"] <= 5e-3 and c32:
                 ok = True
                 note += " -> precision-chaotic, agrees with the twin"
+            else:
+                # the proof tests/test_fuzz_gpu.py demands: every over-tolerance pixel that is not an edge flip lies where the
+                # oracle's own f64 and f32 modes disagree (or the device equals the twin), and the ray counts agree with the
+                # twin or the two oracle modes disagree with EACH OTHER by more than the tolerance
+                from util import TOL, _nbhd_min_max
+                a = np.asarray(img, np.float64).reshape(h, w, 3)
+                b = np.asarray(ref, np.float64).reshape(h, w, 3)
+                c = np.asarray(ref32, np.float64).reshape(h, w, 3)
+                lo, hi = _nbhd_min_max(b)
+                over = np.abs(a - b).max(axis=2) > TOL
+                flip = over & ((((hi - lo).max(axis=2) > 2 * TOL) & ((a >= lo - TOL) & (a <= hi + TOL)).all(axis=2)) | ((hi - lo).max(axis=2) > 0.1))
+                unproven = over & ~flip & ~((np.abs(b - c).max(axis=2) > TOL) | (np.abs(a - c).max(axis=2) <= TOL))
+                oracles_differ = not all(abs(int(getattr(ost32, k)) - int(getattr(ost, k))) <= max(6, 5e-3 * int(getattr(ost, k))) for k in keys)
+                if not unproven.any() and (c32 or oracles_differ):
+                    ok = True
+                    note += " -> precision-chaotic: 0 unproven pixels, the f64 and f32 oracles disagree with each other"
+                else:
+                    note += " -> %d unproven pixels, oracle modes %s on the counts" % (int(unproven.sum()), "disagree" if oracles_differ else "AGREE")
         bad += 0 if ok else 1
         print("%3d %s %dx%dx%d nodes=%d lights=%d knobs=%s frac_over=%.4f max=%.3f rays=%d/%d culled=%d %s" % (
             i, "ok " if ok else "BAD", w, h, spp, len(nodes), len(lights), ",".join(knobs) or "-", m["frac_over"], m["max_abs"],
