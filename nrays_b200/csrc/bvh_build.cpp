@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
 #include <thread>
 
 namespace nrb {
@@ -72,9 +74,16 @@ int BvhBuilder::build_triangles(std::vector<BuildItem> &items, Box *root_box) {
   // on worker threads into private pools, then splice them into the shared pool.
   std::vector<Task> tasks;
   tasks_ = &tasks;
-  task_size_ = std::max<size_t>(16384, items.size() / (8 * (size_t)hw));
+  // subtrees per thread: the levels between the threaded passes (>= kParallelPass items) and the task size run on THIS thread
+  // alone, so few, large tasks win (C4 on 16 cores: top of the tree 423 / 379 / 329 / 279 ms at 8 / 4 / 2 / 1, subtrees 107 /
+  // 116 / 126 / 160 ms)
+  size_t task_div = 2;
+  if (const char *e = getenv("NRB_BVH_TASK_DIV")) task_div = (size_t)std::max(1, atoi(e));
+  task_size_ = std::max<size_t>(16384, items.size() / (task_div * (size_t)hw));
+  auto T0 = std::chrono::steady_clock::now();
   int root = build_rec(items.data(), items.size(), false, 0, root_box);
   tasks_ = nullptr;
+  auto T1 = std::chrono::steady_clock::now();
   std::vector<BvhBuilder> subs(tasks.size());
   std::vector<int> sub_root(tasks.size());
   std::vector<int> sub_depth(tasks.size(), 0);
@@ -93,6 +102,7 @@ int BvhBuilder::build_triangles(std::vector<BuildItem> &items, Box *root_box) {
     for (unsigned t = 0; t < std::min<unsigned>(hw, (unsigned)tasks.size()); ++t) pool.emplace_back(worker);
     for (auto &t : pool) t.join();
   }
+  auto T2 = std::chrono::steady_clock::now();
   // splice: shift node indices and leaf triangle offsets of each private pool (every pool copied by a worker thread)
   std::vector<int> resolved(tasks.size());
   std::vector<size_t> node_at(tasks.size() + 1), tri_at(tasks.size() + 1);
@@ -142,6 +152,12 @@ int BvhBuilder::build_triangles(std::vector<BuildItem> &items, Box *root_box) {
     fix(n.n3.y);
   }
   fix(root);
+  if (getenv("NRB_BUILD_TIMES")) {
+    auto T3 = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "[nrb] build:   SAH: top of the tree %.1f ms (%zu subtrees), subtrees %.1f ms, splice %.1f ms\n", ms(T0, T1), tasks.size(),
+            ms(T1, T2), ms(T2, T3));
+  }
   return root;
 }
 
