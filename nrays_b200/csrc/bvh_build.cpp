@@ -213,36 +213,51 @@ int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, B
   int best_axis = -1, best_bin = -1;
   float best_cost = 3.402823466e+38f;
   if (depth < kForceMedianDepth) {
+    // one sweep over the items fills the bins of all three axes (the items of the large nodes stream from DRAM)
+    Box bb3[3][kBins];
+    size_t cnt3[3][kBins];
+    float lo3[3], scale3[3];
+    bool use3[3];
     for (int axis = 0; axis < 3; ++axis) {
-      float lo = cbounds.lo[axis], ext = cbounds.hi[axis] - cbounds.lo[axis];
-      if (!(ext > 0.0f)) continue;
-      Box bb[kBins];
-      size_t cnt[kBins];
-      for (int b = 0; b < kBins; ++b) bb[b].reset(), cnt[b] = 0;
-      float scale = (float)kBins * (1.0f - 1e-6f) / ext;
-      auto bin_items = [&](size_t lo_i, size_t hi_i, Box *tb, size_t *tc) {
-        for (size_t i = lo_i; i < hi_i; ++i) {
-          int b = (int)((centroid(items[i].box, axis) - lo) * scale);
+      const float ext = cbounds.hi[axis] - cbounds.lo[axis];
+      use3[axis] = ext > 0.0f;
+      lo3[axis] = cbounds.lo[axis];
+      scale3[axis] = use3[axis] ? (float)kBins * (1.0f - 1e-6f) / ext : 0.0f;
+      for (int b = 0; b < kBins; ++b) bb3[axis][b].reset(), cnt3[axis][b] = 0;
+    }
+    auto bin_items = [&](size_t lo_i, size_t hi_i, Box (*tb)[kBins], size_t (*tc)[kBins]) {
+      for (size_t i = lo_i; i < hi_i; ++i) {
+        const Box &bx = items[i].box;
+        for (int axis = 0; axis < 3; ++axis) {
+          if (!use3[axis]) continue;
+          int b = (int)((centroid(bx, axis) - lo3[axis]) * scale3[axis]);
           b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
-          tb[b].grow(items[i].box);
-          tc[b]++;
+          tb[axis][b].grow(bx);
+          tc[axis][b]++;
         }
-      };
-      if (hw > 1) {
-        struct ThreadBins {
-          Box bb[kBins];
-          size_t cnt[kBins];
-        };
-        std::vector<ThreadBins> tb(hw);
-        for (auto &t : tb)
-          for (int b = 0; b < kBins; ++b) t.bb[b].reset(), t.cnt[b] = 0;
-        chunked(n, hw, [&](unsigned t, size_t lo_i, size_t hi_i) { bin_items(lo_i, hi_i, tb[t].bb, tb[t].cnt); });
-        for (auto &t : tb)
-          for (int b = 0; b < kBins; ++b)
-            if (t.cnt[b]) bb[b].grow(t.bb[b]), cnt[b] += t.cnt[b];
-      } else {
-        bin_items(0, n, bb, cnt);
       }
+    };
+    if (hw > 1) {
+      struct ThreadBins {
+        Box bb[3][kBins];
+        size_t cnt[3][kBins];
+      };
+      std::vector<ThreadBins> tb(hw);
+      for (auto &t : tb)
+        for (int axis = 0; axis < 3; ++axis)
+          for (int b = 0; b < kBins; ++b) t.bb[axis][b].reset(), t.cnt[axis][b] = 0;
+      chunked(n, hw, [&](unsigned t, size_t lo_i, size_t hi_i) { bin_items(lo_i, hi_i, tb[t].bb, tb[t].cnt); });
+      for (auto &t : tb)
+        for (int axis = 0; axis < 3; ++axis)
+          for (int b = 0; b < kBins; ++b)
+            if (t.cnt[axis][b]) bb3[axis][b].grow(t.bb[axis][b]), cnt3[axis][b] += t.cnt[axis][b];
+    } else {
+      bin_items(0, n, bb3, cnt3);
+    }
+    for (int axis = 0; axis < 3; ++axis) {
+      if (!use3[axis]) continue;
+      const Box *bb = bb3[axis];
+      const size_t *cnt = cnt3[axis];
       float right_area[kBins];
       size_t right_cnt[kBins];
       Box acc;
@@ -275,12 +290,53 @@ int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, B
   if (best_axis >= 0) {
     float lo = cbounds.lo[best_axis], ext = cbounds.hi[best_axis] - cbounds.lo[best_axis];
     float scale = (float)kBins * (1.0f - 1e-6f) / ext;
-    BuildItem *m = std::partition(items, items + n, [&](const BuildItem &it) {
+    auto left = [&](const BuildItem &it) {
       int b = (int)((centroid(it.box, best_axis) - lo) * scale);
       b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
       return b <= best_bin;
-    });
-    mid = (size_t)(m - items);
+    };
+    if (n >= kParallelPass) {
+      // Large node: a STABLE partition through a scratch array — counts per chunk, prefix, scatter, copy back — so the
+      // result does not depend on how many threads share the work (std::partition's order would).  The size test alone
+      // picks this path: a single-threaded build takes it too and produces the same tree.
+      const unsigned pw = std::max(1u, hw);
+      if (scratch_n_ < n) {
+        scratch_.reset(new BuildItem[n]);
+        scratch_n_ = n;
+      }
+      BuildItem *tmp = scratch_.get();
+      std::vector<size_t> n_left(pw + 1, 0), lo_of(pw + 1, 0);
+      const size_t chunk = (n + pw - 1) / pw;
+      for (unsigned t = 0; t <= pw; ++t) lo_of[t] = std::min(n, (size_t)t * chunk);
+      auto count_chunk = [&](unsigned t, size_t lo_i, size_t hi_i) {
+        size_t c = 0;
+        for (size_t i = lo_i; i < hi_i; ++i) c += left(items[i]) ? 1 : 0;
+        n_left[t + 1] = c;
+      };
+      if (pw > 1) chunked(n, pw, count_chunk);
+      else count_chunk(0, 0, n);
+      for (unsigned t = 0; t < pw; ++t) n_left[t + 1] += n_left[t];  // left items in front of chunk t + 1
+      const size_t total_left = n_left[pw];
+      auto scatter_chunk = [&](unsigned t, size_t lo_i, size_t hi_i) {
+        size_t l = n_left[t], r = total_left + (lo_i - n_left[t]);
+        for (size_t i = lo_i; i < hi_i; ++i) {
+          if (left(items[i])) tmp[l++] = items[i];
+          else tmp[r++] = items[i];
+        }
+      };
+      auto copy_chunk = [&](unsigned, size_t lo_i, size_t hi_i) { std::memcpy(items + lo_i, tmp + lo_i, (hi_i - lo_i) * sizeof(BuildItem)); };
+      if (pw > 1) {
+        chunked(n, pw, scatter_chunk);
+        chunked(n, pw, copy_chunk);
+      } else {
+        scatter_chunk(0, 0, n);
+        copy_chunk(0, 0, n);
+      }
+      mid = total_left;
+    } else {
+      BuildItem *m = std::partition(items, items + n, left);
+      mid = (size_t)(m - items);
+    }
   } else {
     mid = 0;
   }

@@ -3,6 +3,7 @@
 // results, so the device tree is a binned-SAH BVH2 in the 64-byte two-box node layout.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <vector>
 
 #include "device_types.cuh"
@@ -62,6 +63,8 @@ struct BvhBuilder {
   int build_rec(BuildItem *items, size_t n, bool payload, int depth, Box *out_box);
   std::vector<Task> *tasks_ = nullptr;  // non-null while the top of a large tree is being split
   size_t task_size_ = 0;
+  std::unique_ptr<BuildItem[]> scratch_;  // stable partition of large nodes
+  size_t scratch_n_ = 0;
 };
 
 // widen a box by a few ulps so f32 slab tests stay conservative w.r.t. the triangle test
