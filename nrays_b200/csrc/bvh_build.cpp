@@ -165,7 +165,8 @@ int BvhBuilder::build_payloads(std::vector<BuildItem> &items, Box *root_box) {
   return build_rec(items.data(), items.size(), true, 0, root_box);
 }
 
-int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, Box *out_box) {
+int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, Box *out_box, const Box *known_bounds,
+                          const Box *known_cbounds) {
   if (depth > max_depth_seen) max_depth_seen = depth;
   Box bounds, cbounds;
   bounds.reset();
@@ -182,7 +183,9 @@ int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, B
       cb.grow(c);
     }
   };
-  if (hw > 1) {
+  if (known_bounds) {
+    bounds = *known_bounds, cbounds = *known_cbounds;  // the parent's bins already hold them
+  } else if (hw > 1) {
     std::vector<Box> pb(hw), pc(hw);
     for (unsigned t = 0; t < hw; ++t) pb[t].reset(), pc[t].reset();
     chunked(n, hw, [&](unsigned t, size_t lo_i, size_t hi_i) { grow_bounds(lo_i, hi_i, pb[t], pc[t]); });
@@ -212,12 +215,20 @@ int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, B
   // ---- choose a split ---------------------------------------------------------------------
   int best_axis = -1, best_bin = -1;
   float best_cost = 3.402823466e+38f;
+  // one sweep over the items fills the bins of all three axes (the items of the large nodes stream from DRAM)
+  Box bb3[3][kBins];
+  size_t cnt3[3][kBins];
+  float lo3[3], scale3[3];
+  bool use3[3];
+  // large nodes also bin the centroids and keep the per-chunk counts: the children's boxes and the partition's chunk
+  // offsets then come out of the bins instead of two more sweeps over the items
+  const bool big = n >= kParallelPass;
+  Box cb3[3][kBins];
+  std::vector<size_t> chunk_cnt;  // [chunk][axis][bin] of the threaded sweep
   if (depth < kForceMedianDepth) {
-    // one sweep over the items fills the bins of all three axes (the items of the large nodes stream from DRAM)
-    Box bb3[3][kBins];
-    size_t cnt3[3][kBins];
-    float lo3[3], scale3[3];
-    bool use3[3];
+    if (big)
+      for (int axis = 0; axis < 3; ++axis)
+        for (int b = 0; b < kBins; ++b) cb3[axis][b].reset();
     for (int axis = 0; axis < 3; ++axis) {
       const float ext = cbounds.hi[axis] - cbounds.lo[axis];
       use3[axis] = ext > 0.0f;
@@ -225,34 +236,44 @@ int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, B
       scale3[axis] = use3[axis] ? (float)kBins * (1.0f - 1e-6f) / ext : 0.0f;
       for (int b = 0; b < kBins; ++b) bb3[axis][b].reset(), cnt3[axis][b] = 0;
     }
-    auto bin_items = [&](size_t lo_i, size_t hi_i, Box (*tb)[kBins], size_t (*tc)[kBins]) {
+    auto bin_items = [&](size_t lo_i, size_t hi_i, Box (*tb)[kBins], size_t (*tc)[kBins], Box (*tcb)[kBins]) {
       for (size_t i = lo_i; i < hi_i; ++i) {
         const Box &bx = items[i].box;
+        const float c[3] = {centroid(bx, 0), centroid(bx, 1), centroid(bx, 2)};
         for (int axis = 0; axis < 3; ++axis) {
           if (!use3[axis]) continue;
-          int b = (int)((centroid(bx, axis) - lo3[axis]) * scale3[axis]);
+          int b = (int)((c[axis] - lo3[axis]) * scale3[axis]);
           b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
           tb[axis][b].grow(bx);
           tc[axis][b]++;
+          if (tcb) tcb[axis][b].grow(c);
         }
       }
     };
     if (hw > 1) {
       struct ThreadBins {
         Box bb[3][kBins];
+        Box cb[3][kBins];
         size_t cnt[3][kBins];
       };
       std::vector<ThreadBins> tb(hw);
       for (auto &t : tb)
         for (int axis = 0; axis < 3; ++axis)
-          for (int b = 0; b < kBins; ++b) t.bb[axis][b].reset(), t.cnt[axis][b] = 0;
-      chunked(n, hw, [&](unsigned t, size_t lo_i, size_t hi_i) { bin_items(lo_i, hi_i, tb[t].bb, tb[t].cnt); });
-      for (auto &t : tb)
+          for (int b = 0; b < kBins; ++b) t.bb[axis][b].reset(), t.cb[axis][b].reset(), t.cnt[axis][b] = 0;
+      chunked(n, hw, [&](unsigned t, size_t lo_i, size_t hi_i) { bin_items(lo_i, hi_i, tb[t].bb, tb[t].cnt, big ? tb[t].cb : nullptr); });
+      chunk_cnt.assign((size_t)hw * 3 * kBins, 0);
+      for (unsigned ti = 0; ti < hw; ++ti) {
+        const ThreadBins &t = tb[ti];
         for (int axis = 0; axis < 3; ++axis)
-          for (int b = 0; b < kBins; ++b)
-            if (t.cnt[axis][b]) bb3[axis][b].grow(t.bb[axis][b]), cnt3[axis][b] += t.cnt[axis][b];
+          for (int b = 0; b < kBins; ++b) {
+            chunk_cnt[((size_t)ti * 3 + axis) * kBins + b] = t.cnt[axis][b];
+            if (!t.cnt[axis][b]) continue;
+            bb3[axis][b].grow(t.bb[axis][b]), cnt3[axis][b] += t.cnt[axis][b];
+            if (big) cb3[axis][b].grow(t.cb[axis][b]);
+          }
+      }
     } else {
-      bin_items(0, n, bb3, cnt3);
+      bin_items(0, n, bb3, cnt3, big ? cb3 : nullptr);
     }
     for (int axis = 0; axis < 3; ++axis) {
       if (!use3[axis]) continue;
@@ -305,17 +326,14 @@ int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, B
         scratch_n_ = n;
       }
       BuildItem *tmp = scratch_.get();
-      std::vector<size_t> n_left(pw + 1, 0), lo_of(pw + 1, 0);
-      const size_t chunk = (n + pw - 1) / pw;
-      for (unsigned t = 0; t <= pw; ++t) lo_of[t] = std::min(n, (size_t)t * chunk);
-      auto count_chunk = [&](unsigned t, size_t lo_i, size_t hi_i) {
+      // left items per chunk: the bins of the sweep above were filled chunk by chunk, with the same chunks
+      std::vector<size_t> n_left(pw + 1, 0);
+      for (unsigned t = 0; t < pw; ++t) {
         size_t c = 0;
-        for (size_t i = lo_i; i < hi_i; ++i) c += left(items[i]) ? 1 : 0;
-        n_left[t + 1] = c;
-      };
-      if (pw > 1) chunked(n, pw, count_chunk);
-      else count_chunk(0, 0, n);
-      for (unsigned t = 0; t < pw; ++t) n_left[t + 1] += n_left[t];  // left items in front of chunk t + 1
+        for (int b = 0; b <= best_bin; ++b)
+          c += pw > 1 ? chunk_cnt[((size_t)t * 3 + best_axis) * kBins + b] : cnt3[best_axis][b];
+        n_left[t + 1] = n_left[t] + c;  // left items in front of chunk t + 1
+      }
       const size_t total_left = n_left[pw];
       auto scatter_chunk = [&](unsigned t, size_t lo_i, size_t hi_i) {
         size_t l = n_left[t], r = total_left + (lo_i - n_left[t]);
@@ -340,7 +358,9 @@ int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, B
   } else {
     mid = 0;
   }
+  bool from_bins = best_axis >= 0;
   if (mid == 0 || mid == n) {
+    from_bins = false;
     // degenerate (coincident centroids) or forced: balanced median split on the widest centroid axis
     int axis = 0;
     float e0 = cbounds.hi[0] - cbounds.lo[0], e1 = cbounds.hi[1] - cbounds.lo[1], e2 = cbounds.hi[2] - cbounds.lo[2];
@@ -356,8 +376,18 @@ int BvhBuilder::build_rec(BuildItem *items, size_t n, bool payload, int depth, B
   nodes.emplace_back();
   std::memset(&nodes[idx], 0, sizeof(BvhNode));
   Box b0, b1;
-  int c0 = build_rec(items, mid, payload, depth + 1, &b0);
-  int c1 = build_rec(items + mid, n - mid, payload, depth + 1, &b1);
+  Box kb[2], kc[2];
+  const bool known = big && from_bins;
+  if (known) {
+    for (int side = 0; side < 2; ++side) kb[side].reset(), kc[side].reset();
+    for (int b = 0; b < kBins; ++b) {
+      if (!cnt3[best_axis][b]) continue;
+      const int side = b <= best_bin ? 0 : 1;
+      kb[side].grow(bb3[best_axis][b]), kc[side].grow(cb3[best_axis][b]);
+    }
+  }
+  int c0 = build_rec(items, mid, payload, depth + 1, &b0, known ? &kb[0] : nullptr, known ? &kc[0] : nullptr);
+  int c1 = build_rec(items + mid, n - mid, payload, depth + 1, &b1, known ? &kb[1] : nullptr, known ? &kc[1] : nullptr);
   BvhNode &nd = nodes[idx];
   set_child_box(nd, 0, b0);
   set_child_box(nd, 1, b1);

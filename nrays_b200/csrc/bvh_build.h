@@ -60,7 +60,9 @@ struct BvhBuilder {
     int depth;
     int placeholder;  // child code written into the parent until the subtree is merged
   };
-  int build_rec(BuildItem *items, size_t n, bool payload, int depth, Box *out_box);
+  // known_bounds / known_cbounds: box and centroid box of the items when the parent already has them (large nodes)
+  int build_rec(BuildItem *items, size_t n, bool payload, int depth, Box *out_box, const Box *known_bounds = nullptr,
+                const Box *known_cbounds = nullptr);
   std::vector<Task> *tasks_ = nullptr;  // non-null while the top of a large tree is being split
   size_t task_size_ = 0;
   std::unique_ptr<BuildItem[]> scratch_;  // stable partition of large nodes
